@@ -1,0 +1,494 @@
+// hfa_api.cu -- host side of libhfa_align.so: length-bucketed collation ("plan") and the C ABI
+// declared in include/hfa_align.h.  No torch types, no device allocation, no stream sync.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <vector>
+
+#include "../../include/hfa_align.h"
+#include "hfa_common.cuh"
+
+#define HFA_EMIS_ROWS 64
+
+cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
+                               float *dp_dump);
+cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp,
+                              float *dp_dump);
+cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype);
+cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const float *prob_log,
+                            const float *edge_log, const float *not_edge_log,
+                            const float *edge_pred);
+cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
+                                 const HfaResultPtrs &res, float *frame_conf, float *dp_path);
+cudaError_t hfa_launch_unpack_bp(const HfaLaunchCtx &c, int utt, int8_t *out);
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(HFA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// side streams for the concurrent per-class DP launches: one set per (host thread, device)
+struct HfaSideStreams {
+    int device = -1;
+    cudaStream_t stream[HFA_NUM_CLASSES] = {};
+    cudaEvent_t fork = nullptr, join[HFA_NUM_CLASSES] = {};
+};
+HfaSideStreams *side_streams()
+{
+    thread_local std::vector<HfaSideStreams *> pool;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (HfaSideStreams *s : pool)
+        if (s->device == dev) return s;
+    HfaSideStreams *s = new (std::nothrow) HfaSideStreams();
+    if (!s) return nullptr;
+    s->device = dev;
+    bool ok = cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < HFA_NUM_CLASSES; ++i) {
+        ok = cudaStreamCreateWithFlags(&s->stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { delete s; return nullptr; }
+    pool.push_back(s);
+    return s;
+}
+
+}  // namespace
+
+// Workspace layout (byte offsets from the workspace base, every region 256-byte aligned):
+//   [utt table][ids][order lists][row_blocks][inputs]   <- "head", uploaded from the plan
+//   [emis][edge2][edge_p][bp][path_state][rev_idx][rev_t][dp_last]
+struct hfa_plan {
+    int32_t n_utt = 0, vocab = 0;
+    double frame_length = 0.0;
+    std::vector<HfaUtt> utt;
+    std::vector<int32_t> ids;
+    std::vector<int64_t> frame_off, seg_off;   // [n+1]
+    // bucket lists: class c = K-1 for the warp kernel (K states per lane), class 8 = CTA kernel,
+    // then the backtrace list (valid utterances by descending T, then the invalid ones)
+    std::vector<int32_t> order;                // concatenation of all lists
+    int32_t class_begin[HFA_NUM_CLASSES + 2] = {0};
+    int32_t class_count[HFA_NUM_CLASSES + 1] = {0};
+    int32_t cta_max_sp = 0, max_sp = 4;
+    int32_t bt_begin = 0;
+    std::vector<int32_t> row_blocks;           // [n+1]
+    int64_t total_frames = 0, total_states = 0, total_cells = 0, padded_cells = 0;
+    int64_t total_words = 0, total_edge = 0;
+    // byte offsets
+    int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_inputs = 0, head_bytes = 0;
+    int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
+            o_last = 0, ws_bytes = 0;
+    std::vector<unsigned char> head;           // host image of the head (without inputs)
+    HfaResultLayout res{};
+};
+
+namespace {
+
+HfaWs make_ws(const hfa_plan *p, void *workspace)
+{
+    unsigned char *b = static_cast<unsigned char *>(workspace);
+    HfaWs w;
+    w.utt = reinterpret_cast<const HfaUtt *>(b + p->o_utt);
+    w.ids = reinterpret_cast<const int32_t *>(b + p->o_ids);
+    w.order = reinterpret_cast<const int32_t *>(b + p->o_order);
+    w.row_blocks = reinterpret_cast<const int32_t *>(b + p->o_rowblk);
+    w.inputs = reinterpret_cast<HfaInput *>(b + p->o_inputs);
+    w.emis = reinterpret_cast<float *>(b + p->o_emis);
+    w.edge2 = reinterpret_cast<float2 *>(b + p->o_edge2);
+    w.edge_p = reinterpret_cast<float *>(b + p->o_edgep);
+    w.bp = reinterpret_cast<uint32_t *>(b + p->o_bp);
+    w.path_state = reinterpret_cast<int32_t *>(b + p->o_path);
+    w.rev_idx = reinterpret_cast<int32_t *>(b + p->o_revi);
+    w.rev_t = reinterpret_cast<int32_t *>(b + p->o_revt);
+    w.dp_last = reinterpret_cast<float *>(b + p->o_last);
+    return w;
+}
+
+HfaLaunchCtx make_ctx(const hfa_plan *p, void *workspace, void *stream)
+{
+    HfaLaunchCtx c;
+    c.ws = make_ws(p, workspace);
+    c.n_utt = p->n_utt;
+    c.vocab = p->vocab;
+    c.frame_length = p->frame_length;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return c;
+}
+
+HfaResultPtrs make_res(const hfa_plan *p, void *result)
+{
+    unsigned char *b = static_cast<unsigned char *>(result);
+    HfaResultPtrs r;
+    r.status = reinterpret_cast<int32_t *>(b + p->res.status);
+    r.n_seg = reinterpret_cast<int32_t *>(b + p->res.n_seg);
+    r.end_state = reinterpret_cast<int32_t *>(b + p->res.end_state);
+    r.final_score = reinterpret_cast<float *>(b + p->res.final_score);
+    r.total_conf = reinterpret_cast<float *>(b + p->res.total_conf);
+    r.ph_idx_seq = reinterpret_cast<int32_t *>(b + p->res.ph_idx_seq);
+    r.ph_time_int = reinterpret_cast<int32_t *>(b + p->res.ph_time_int);
+    r.intervals = reinterpret_cast<double *>(b + p->res.intervals);
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hfa_abi_version(void) { return HFA_ABI_VERSION; }
+const char *hfa_last_error(void) { return g_err; }
+int64_t hfa_launch_count(void) { return g_launches.load(); }
+
+int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const int32_t *S,
+                    const int32_t *ph_ids, double frame_length, hfa_plan **out)
+{
+    if (out == nullptr) return fail(HFA_ERR_ARG, "hfa_plan_create: out is NULL");
+    *out = nullptr;
+    if (n_utt < 0 || vocab_size < 1 || (n_utt > 0 && (!T || !S || !ph_ids)))
+        return fail(HFA_ERR_ARG, "hfa_plan_create: bad arguments (n_utt=%d, V=%d)", n_utt,
+                    vocab_size);
+    hfa_plan *p = new (std::nothrow) hfa_plan();
+    if (!p) return fail(HFA_ERR_NOMEM, "hfa_plan_create: out of host memory");
+    try {
+        p->n_utt = n_utt;
+        p->vocab = vocab_size;
+        p->frame_length = frame_length;
+        p->utt.resize((size_t)n_utt);
+        p->frame_off.assign((size_t)n_utt + 1, 0);
+        p->seg_off.assign((size_t)n_utt + 1, 0);
+        p->row_blocks.assign((size_t)n_utt + 1, 0);
+        for (int32_t b = 0; b < n_utt; ++b)
+            p->seg_off[b + 1] = p->seg_off[b] + std::max<int32_t>(S[b], 0);
+        p->total_states = p->seg_off[n_utt];
+        p->ids.assign(ph_ids, ph_ids + p->total_states);
+
+        std::vector<int32_t> lists[HFA_NUM_CLASSES + 1], invalid;
+        int64_t emis = 0, edge = 0, words = 0, cells = 0, frames = 0;
+        for (int32_t b = 0; b < n_utt; ++b) {
+            HfaUtt &m = p->utt[b];
+            std::memset(&m, 0, sizeof(m));
+            const int32_t t = T[b], s = S[b];
+            int32_t st = HFA_UTT_OK;
+            if (s < 1) st = HFA_UTT_NO_STATES;
+            else if (t < 1) st = HFA_UTT_EMPTY;
+            else if (s > HFA_MAX_STATES) st = HFA_UTT_TOO_MANY_STATES;
+            else {
+                const int32_t *id = ph_ids + p->seg_off[b];
+                for (int32_t i = 0; i < s; ++i)
+                    if (id[i] < 0 || id[i] >= vocab_size) { st = HFA_UTT_BAD_ID; break; }
+            }
+            m.status = st;
+            m.seg_off = p->seg_off[b];
+            m.frame_off = frames;
+            m.cell_off = cells;
+            m.emis_off = emis;
+            m.edge_off = edge;
+            m.bp_off = words;
+            p->frame_off[b] = frames;
+            if (st == HFA_UTT_OK) {
+                m.T = t;
+                m.S = s;
+                m.Sp = (s + 3) & ~3;
+                frames += t;
+                cells += (int64_t)t * s;
+                emis += (int64_t)t * m.Sp;
+                edge += align_up(t, HFA_TILE_T);
+                words += (int64_t)((t + 15) / 16) * m.Sp;
+                p->row_blocks[b + 1] = p->row_blocks[b] + (t + HFA_EMIS_ROWS - 1) / HFA_EMIS_ROWS;
+                p->max_sp = std::max(p->max_sp, m.Sp);
+                if (m.Sp <= HFA_WARP_MAX_S) lists[(m.Sp + 31) / 32 - 1].push_back(b);
+                else {
+                    lists[HFA_NUM_CLASSES].push_back(b);
+                    p->cta_max_sp = std::max(p->cta_max_sp, m.Sp);
+                }
+            } else {
+                p->row_blocks[b + 1] = p->row_blocks[b];
+                invalid.push_back(b);
+            }
+        }
+        p->frame_off[n_utt] = frames;
+        p->total_frames = frames;
+        p->total_cells = cells;
+        p->padded_cells = emis;
+        p->total_words = words;
+        p->total_edge = edge;
+
+        // longest utterances first inside every bucket (they bound the tail of the launch)
+        auto by_len = [&](int32_t a, int32_t b) {
+            return p->utt[a].T != p->utt[b].T ? p->utt[a].T > p->utt[b].T : a < b;
+        };
+        std::vector<int32_t> all;
+        for (int c = 0; c <= HFA_NUM_CLASSES; ++c) {
+            std::sort(lists[c].begin(), lists[c].end(), by_len);
+            p->class_begin[c] = (int32_t)p->order.size();
+            p->class_count[c] = (int32_t)lists[c].size();
+            p->order.insert(p->order.end(), lists[c].begin(), lists[c].end());
+            all.insert(all.end(), lists[c].begin(), lists[c].end());
+        }
+        std::sort(all.begin(), all.end(), by_len);
+        p->bt_begin = (int32_t)p->order.size();
+        p->order.insert(p->order.end(), all.begin(), all.end());
+        p->order.insert(p->order.end(), invalid.begin(), invalid.end());
+
+        // workspace layout
+        int64_t o = 0;
+        auto region = [&](int64_t bytes) { const int64_t at = o; o = align_up(o + bytes, 256); return at; };
+        p->o_utt = region((int64_t)n_utt * sizeof(HfaUtt));
+        p->o_ids = region(p->total_states * 4);
+        p->o_order = region((int64_t)p->order.size() * 4);
+        p->o_rowblk = region((int64_t)(n_utt + 1) * 4);
+        p->head_bytes = o;
+        p->o_inputs = region((int64_t)n_utt * sizeof(HfaInput));
+        p->o_emis = region(emis * 4);
+        p->o_edge2 = region(edge * 8);
+        p->o_edgep = region(edge * 4 + 4);      // +1: seg_time reads p[t+1] only when t+1 < T
+        p->o_bp = region(words * 4);
+        p->o_path = region(frames * 4);
+        p->o_revi = region(p->total_states * 4);
+        p->o_revt = region(p->total_states * 4);
+        p->o_last = region((int64_t)n_utt * 8);
+        p->ws_bytes = std::max<int64_t>(o, 256);
+
+        p->head.assign((size_t)p->head_bytes, 0);
+        if (n_utt > 0) {
+            std::memcpy(p->head.data() + p->o_utt, p->utt.data(), (size_t)n_utt * sizeof(HfaUtt));
+            if (p->total_states)
+                std::memcpy(p->head.data() + p->o_ids, p->ids.data(), (size_t)p->total_states * 4);
+            std::memcpy(p->head.data() + p->o_order, p->order.data(), p->order.size() * 4);
+        }
+        std::memcpy(p->head.data() + p->o_rowblk, p->row_blocks.data(), (size_t)(n_utt + 1) * 4);
+
+        // result blob layout
+        int64_t r = 0;
+        auto rreg = [&](int64_t bytes) { const int64_t at = r; r = align_up(r + bytes, 16); return at; };
+        p->res.status = rreg((int64_t)n_utt * 4);
+        p->res.n_seg = rreg((int64_t)n_utt * 4);
+        p->res.end_state = rreg((int64_t)n_utt * 4);
+        p->res.final_score = rreg((int64_t)n_utt * 4);
+        p->res.total_conf = rreg((int64_t)n_utt * 4);
+        p->res.ph_idx_seq = rreg(p->total_states * 4);
+        p->res.ph_time_int = rreg(p->total_states * 4);
+        p->res.intervals = rreg(p->total_states * 16);
+        p->res.total_bytes = std::max<int64_t>(r, 16);
+    } catch (const std::bad_alloc &) {
+        delete p;
+        return fail(HFA_ERR_NOMEM, "hfa_plan_create: out of host memory");
+    }
+    *out = p;
+    return HFA_OK;
+}
+
+void hfa_plan_destroy(hfa_plan *plan) { delete plan; }
+
+int64_t hfa_plan_workspace_bytes(const hfa_plan *p) { return p ? p->ws_bytes : 0; }
+int64_t hfa_plan_total_frames(const hfa_plan *p) { return p ? p->total_frames : 0; }
+int64_t hfa_plan_total_states(const hfa_plan *p) { return p ? p->total_states : 0; }
+int64_t hfa_plan_total_cells(const hfa_plan *p) { return p ? p->total_cells : 0; }
+const int64_t *hfa_plan_frame_offsets(const hfa_plan *p) { return p ? p->frame_off.data() : nullptr; }
+const int64_t *hfa_plan_seg_offsets(const hfa_plan *p) { return p ? p->seg_off.data() : nullptr; }
+
+int hfa_plan_result_layout(const hfa_plan *p, HfaResultLayout *out)
+{
+    if (!p || !out) return fail(HFA_ERR_ARG, "hfa_plan_result_layout: NULL argument");
+    *out = p->res;
+    return HFA_OK;
+}
+
+int hfa_plan_algorithmic_bytes(const hfa_plan *p, int32_t dtype, int64_t out[3])
+{
+    if (!p || !out) return fail(HFA_ERR_ARG, "hfa_plan_algorithmic_bytes: NULL argument");
+    const int64_t in_b = (dtype == HFA_DTYPE_F32) ? 4 : 2;
+    int64_t words = 0;
+    for (const HfaUtt &m : p->utt)
+        if (m.status == 0) words += (int64_t)((m.T + 15) / 16) * m.S;
+    // unpadded figures: emission reads V logits + 1 edge logit per frame and writes
+    // S emissions + {edge_log, not_edge_log, edge_pred}; the DP reads them back and writes 2 bits
+    // per cell; the backtrace reads the path's backpointers and operands and writes the segments.
+    out[0] = p->total_frames * ((int64_t)p->vocab * in_b + in_b) + p->total_cells * 4 +
+             p->total_frames * 12;
+    out[1] = p->total_cells * 4 + p->total_frames * 8 + words * 4;
+    out[2] = p->total_frames * (8 + 8) + p->total_states * 24;
+    return HFA_OK;
+}
+
+int64_t hfa_plan_debug_region(const hfa_plan *p, int32_t which, int64_t *n_bytes)
+{
+    if (!p) return -1;
+    int64_t off = -1, n = 0;
+    switch (which) {
+        case 0: off = p->o_emis; n = p->padded_cells * 4; break;
+        case 1: off = p->o_edge2; n = p->total_edge * 8; break;
+        case 2: off = p->o_edgep; n = p->total_edge * 4; break;
+        case 3: off = p->o_bp; n = p->total_words * 4; break;
+        default: break;
+    }
+    if (n_bytes) *n_bytes = n;
+    return off;
+}
+
+int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_plan_upload: NULL argument");
+    if (p->head_bytes == 0) return HFA_OK;
+    cudaError_t e = cudaMemcpyAsync(workspace, p->head.data(), (size_t)p->head_bytes,
+                                    cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload");
+    return HFA_OK;
+}
+
+int hfa_set_inputs(const hfa_plan *p, void *workspace, const void *const *frame_ptrs,
+                   const int64_t *frame_stride_t, const int64_t *frame_stride_v,
+                   const void *const *edge_ptrs, const int64_t *edge_stride, void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL plan/workspace");
+    if (p->n_utt == 0) return HFA_OK;
+    if (!frame_ptrs || !frame_stride_t || !frame_stride_v || !edge_ptrs || !edge_stride)
+        return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL input table");
+    std::vector<HfaInput> in((size_t)p->n_utt);
+    for (int32_t b = 0; b < p->n_utt; ++b) {
+        if (p->utt[b].status == 0 && (!frame_ptrs[b] || !edge_ptrs[b]))
+            return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL logits pointer for utterance %d", b);
+        in[b].frame = frame_ptrs[b];
+        in[b].edge = edge_ptrs[b];
+        in[b].frame_st = frame_stride_t[b];
+        in[b].frame_sv = frame_stride_v[b];
+        in[b].edge_st = edge_stride[b];
+    }
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    // pageable source: the runtime stages the table before returning, `in` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(c.ws.inputs, in.data(), in.size() * sizeof(HfaInput),
+                                    cudaMemcpyHostToDevice, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_set_inputs: input table upload");
+    return HFA_OK;
+}
+
+int hfa_emission(const hfa_plan *p, void *workspace, int32_t dtype, void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_emission: NULL plan/workspace");
+    if (p->n_utt == 0 || p->total_frames == 0) return HFA_OK;
+    if (dtype < 0 || dtype > 2) return fail(HFA_ERR_ARG, "hfa_emission: bad dtype %d", dtype);
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    cudaError_t e = hfa_launch_emission(c, p->row_blocks[p->n_utt], p->max_sp, dtype);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_emission: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+int hfa_pack_emissions(const hfa_plan *p, void *workspace, const float *prob_log,
+                       const float *edge_log, const float *not_edge_log, const float *edge_pred,
+                       void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_pack_emissions: NULL plan/workspace");
+    if (p->n_utt == 0 || p->total_frames == 0) return HFA_OK;
+    if (!prob_log || !edge_log || !not_edge_log)
+        return fail(HFA_ERR_ARG, "hfa_pack_emissions: NULL input");
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    cudaError_t e = hfa_launch_pack(c, p->row_blocks[p->n_utt], prob_log, edge_log, not_edge_log,
+                                    edge_pred);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_pack_emissions: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_viterbi_forward: NULL plan/workspace");
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    // The state-count classes are independent launches: fork them onto side streams so that the
+    // serial-in-time tails of the classes overlap instead of adding up, then join (capturable).
+    int n_active = 0;
+    for (int k = 0; k <= HFA_NUM_CLASSES; ++k) n_active += p->class_count[k] > 0;
+    if (n_active == 0) return HFA_OK;
+    HfaSideStreams *ss = nullptr;
+    if (n_active > 1) {
+        ss = side_streams();
+        if (!ss) return fail(HFA_ERR_CUDA, "hfa_viterbi_forward: cannot create side streams");
+        cudaError_t e = cudaEventRecord(ss->fork, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: fork record");
+    }
+    const cudaStream_t user = c.stream;
+    int slot = 0;
+    for (int k = 0; k <= HFA_NUM_CLASSES; ++k) {
+        if (p->class_count[k] == 0) continue;
+        cudaError_t e;
+        if (slot > 0) {
+            c.stream = ss->stream[slot - 1];
+            e = cudaStreamWaitEvent(c.stream, ss->fork, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: fork wait");
+        } else {
+            c.stream = user;
+        }
+        if (k < HFA_NUM_CLASSES)
+            e = hfa_launch_dp_warp(c, k + 1, c.ws.order + p->class_begin[k], p->class_count[k],
+                                   dp_dump);
+        else
+            e = hfa_launch_dp_cta(c, c.ws.order + p->class_begin[k], p->class_count[k],
+                                  p->cta_max_sp, dp_dump);
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: kernel launch");
+        g_launches += 1;
+        if (slot > 0) {
+            e = cudaEventRecord(ss->join[slot - 1], c.stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ss->join[slot - 1], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: join");
+        }
+        ++slot;
+    }
+    return HFA_OK;
+}
+
+int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame_conf,
+                  float *dp_path, void *stream)
+{
+    if (!p || !workspace || !result) return fail(HFA_ERR_ARG, "hfa_backtrace: NULL argument");
+    if (p->n_utt == 0) return HFA_OK;
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    const HfaResultPtrs r = make_res(p, result);
+    cudaError_t e = hfa_launch_backtrace(c, c.ws.order + p->bt_begin, p->n_utt, r, frame_conf,
+                                         dp_path);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_backtrace: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+int hfa_align_batch(const hfa_plan *p, void *workspace, int32_t dtype, void *result,
+                    float *frame_conf, void *stream)
+{
+    int rc = hfa_emission(p, workspace, dtype, stream);
+    if (rc != HFA_OK) return rc;
+    rc = hfa_viterbi_forward(p, workspace, nullptr, stream);
+    if (rc != HFA_OK) return rc;
+    return hfa_backtrace(p, workspace, result, frame_conf, nullptr, stream);
+}
+
+int hfa_debug_unpack_backptr(const hfa_plan *p, const void *workspace, int32_t utt, int8_t *out,
+                             void *stream)
+{
+    if (!p || !workspace || !out) return fail(HFA_ERR_ARG, "hfa_debug_unpack_backptr: NULL argument");
+    if (utt < 0 || utt >= p->n_utt || p->utt[utt].status != 0)
+        return fail(HFA_ERR_ARG, "hfa_debug_unpack_backptr: bad utterance %d", utt);
+    HfaLaunchCtx c = make_ctx(p, const_cast<void *>(workspace), stream);
+    cudaError_t e = hfa_launch_unpack_bp(c, utt, out);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_debug_unpack_backptr: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// hfa_backtrace.cu -- end state, backtrace, path rescoring, confidence and frame->interval, on device.
+//
+// Reference: tools/alignment_decoder.py:264-288 (end state, backward walk, frame_confidence),
+// :97 (total_confidence), :104-113 (fractional boundary refinement, seconds).
+//
+// One warp per utterance, three phases:
+//  1. backward walk over the bit-packed backpointers.  A word covers 16 frames of one state and the
+//     path moves down at most 2 states per frame, so one 16-frame word-row only ever needs the 32
+//     states below the state it was entered in: lane j keeps word(row, s_hi - j) in a register, the
+//     walk is shuffle lookups + clz jumps from move to move, and the band of the next row (64 states
+//     wide, it is not yet known where this row ends) is prefetched before the walk starts.
+//  2. forward rescoring of the path.  The reference reads dp[t, s_t] out of the T x S matrix it kept;
+//     we never store dp, and rebuild those T numbers bit-exactly from the path alone: on the best
+//     path curr[] of the state being left equals the running max of its emissions since the path
+//     entered it (0 for SP states, except that nothing is zeroed at t = 0).  Lanes gather the
+//     per-frame operands in parallel, the f32/f64 chain itself runs once per frame (uniform).
+//  3. segments -> seconds (f64), lane-parallel.
+#include "hfa_common.cuh"
+
+#define HFA_BT_WARPS 4
+
+namespace {
+
+__device__ __forceinline__ double seg_time(const float *p, int t, int T, double frame_length)
+{
+    // :83 edge_diff[t] = f64(f32(p[t+1] - p[t])), 0 for the last frame; :104 clip(diff / 2, +-0.5)
+    double d = (t + 1 < T) ? (double)__fsub_rn(p[t + 1], p[t]) : 0.0;
+    d = fmin(fmax(__dmul_rn(d, 0.5), -0.5), 0.5);
+    return __dmul_rn(frame_length, __dadd_rn((double)(float)t, d));   // :105-108
+}
+
+__global__ void __launch_bounds__(HFA_BT_WARPS * 32)
+hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResultPtrs res,
+                     float *__restrict__ frame_conf, float *__restrict__ dp_path,
+                     double frame_length)
+{
+    __shared__ float4 stage_sm[HFA_BT_WARPS][32];
+    __shared__ float dpath_sm[HFA_BT_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * HFA_BT_WARPS + warp;
+    if (item >= n) return;
+    const int u = order[item];
+    const HfaUtt m = ws.utt[u];
+    if (m.status != 0) {                       // invalid utterance: report, produce nothing
+        if (lane == 0) {
+            res.status[u] = m.status;
+            res.n_seg[u] = 0;
+            res.end_state[u] = -1;
+            res.final_score[u] = HFA_NEG_INF;
+            res.total_conf[u] = __uint_as_float(0x7fc00000u);
+        }
+        return;
+    }
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int32_t *ids = ws.ids + m.seg_off;
+    const uint32_t *bp = ws.bp + m.bp_off;
+    int32_t *rev_idx = ws.rev_idx + m.seg_off;
+    int32_t *rev_t = ws.rev_t + m.seg_off;
+    int32_t *path_state = ws.path_state + m.frame_off;
+
+    // ---- end state (:269-272) ----
+    const float last1 = ws.dp_last[2 * u];
+    const float last2 = (S >= 2) ? ws.dp_last[2 * u + 1] : HFA_NEG_INF;
+    int s = S - 1;
+    float final_score = last1;
+    if (S >= 2 && last2 > last1 && ids[S - 1] == 0) {
+        s = S - 2;
+        final_score = last2;
+    }
+    const int s_end = s;
+
+    // ---- phase 1: backward walk ----
+    const int n_rows = (T + 15) >> 4;
+    int n_seg = 0;
+    int s_hi = s;
+    uint32_t W = (s_hi - lane >= 0) ? bp[(int64_t)(n_rows - 1) * Sp + (s_hi - lane)] : 0u;
+    for (int w = n_rows - 1; w >= 0; --w) {
+        uint32_t A = 0u, B = 0u;
+        if (w > 0) {
+            const uint32_t *row = bp + (int64_t)(w - 1) * Sp;
+            if (s_hi - lane >= 0) A = row[s_hi - lane];
+            if (s_hi - 32 - lane >= 0) B = row[s_hi - 32 - lane];
+        }
+        int tt = (w == n_rows - 1) ? ((T - 1) & 15) : 15;
+        int my_state = 0;
+        while (tt >= 0) {
+            const uint32_t wc = __shfl_sync(0xffffffffu, W, (s_hi - s) & 31);
+            uint32_t nz = (wc | (wc >> 16)) & 0xffffu & ((2u << tt) - 1u);
+            if (w == 0) nz |= 1u;                       // frame 0 always opens a segment (:277)
+            if (nz == 0u) {
+                if (lane <= tt) my_state = s;
+                break;
+            }
+            const int tp = 31 - __clz(nz);              // latest frame <= tt where the path moved
+            if (lane <= tt && lane >= tp) my_state = s;
+            if (lane == 0 && n_seg < S) {
+                rev_idx[n_seg] = s;
+                rev_t[n_seg] = 16 * w + tp;
+            }
+            ++n_seg;
+            if (w == 0 && tp == 0) break;
+            s -= ((wc >> (16 + tp)) & 1u) ? 2 : 1;
+            tt = tp - 1;
+        }
+        if (lane < 16 && 16 * w + lane < T) path_state[16 * w + lane] = my_state;
+        if (w > 0) {
+            const int d = s_hi - s;                     // 0..32 states walked down in this row
+            const int src = (d + lane) & 31;
+            const uint32_t x = __shfl_sync(0xffffffffu, A, src);
+            const uint32_t y = __shfl_sync(0xffffffffu, B, src);
+            W = (d + lane < 32) ? x : y;
+            s_hi = s;
+        }
+    }
+    if (n_seg > S) n_seg = S;                           // cannot happen with valid backpointers
+    __syncwarp();
+
+    // ---- phase 2: forward rescoring, frame confidence ----
+    const float *emis = ws.emis + m.emis_off;
+    const float2 *edge2 = ws.edge2 + m.edge_off;
+    const double ratio = __ddiv_rn((double)T, (double)S);
+    const bool lead_sp = (ids[0] == 0) && (S > 1);
+    float4 *stage = stage_sm[warp];
+    float *dpath = dpath_sm[warp];
+    float d = 0.0f, cu = 0.0f, carry_d = 0.0f;          // dp_path[-1] := 0 (:286)
+    int carry_state = 0;
+    double log_sum = 0.0;
+    for (int c0 = 0; c0 < T; c0 += 32) {
+        const int t = c0 + lane;
+        const bool valid = t < T;
+        const int st = valid ? path_state[t] : 0;
+        int sprev = __shfl_up_sync(0xffffffffu, st, 1);
+        if (lane == 0) sprev = (c0 == 0) ? st : carry_state;
+        carry_state = __shfl_sync(0xffffffffu, st, 31);
+        const int s0 = __shfl_sync(0xffffffffu, st, 0);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const float *row = emis + (int64_t)t * Sp;
+            const bool moved = (t > 0) && (sprev != st);
+            const float2 ed = edge2[t];
+            v.x = row[st];
+            v.y = moved ? row[sprev] : v.x;
+            v.z = moved ? ed.x : ed.y;
+            v.w = __int_as_float((moved ? 1 : 0) | ((ids[st] == 0) ? 2 : 0));
+        }
+        stage[lane] = v;
+        __syncwarp();
+        const int cnt = min(32, T - c0);
+        for (int j = 0; j < cnt; ++j) {
+            const float4 q = stage[j];
+            const int fl = __float_as_int(q.w);
+            if (c0 + j == 0) {
+                // :250-254 only state 0 (and state 1 behind a leading SP) are seeded
+                const bool seeded = (s0 == 0) || (s0 == 1 && lead_sp);
+                d = seeded ? q.x : HFA_NEG_INF;
+                cu = d;
+            } else {
+                if (fl & 1) {
+                    d = hfa_advance(__fadd_rn(__fadd_rn(d, q.y), q.z), cu, ratio);
+                    cu = q.x;
+                } else {
+                    d = __fadd_rn(__fadd_rn(d, q.x), q.z);
+                    cu = fmaxf(cu, q.x);
+                }
+                if (fl & 2) cu = 0.0f;
+            }
+            if (lane == 0) dpath[j] = d;
+        }
+        __syncwarp();
+        if (valid) {
+            const float cur = dpath[lane];
+            const float prev = (lane == 0) ? carry_d : dpath[lane - 1];
+            const float fc = expf(__fsub_rn(cur, prev));                 // :284-288
+            if (frame_conf != nullptr) frame_conf[m.frame_off + t] = fc;
+            if (dp_path != nullptr) dp_path[m.frame_off + t] = cur;
+            log_sum += (double)logf(__fadd_rn(fc, 1e-6f));               // :97
+        }
+        carry_d = d;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) log_sum += __shfl_xor_sync(0xffffffffu, log_sum, o);
+    const float mean = (float)(log_sum / (double)T);
+    const float total = expf(__fdiv_rn(mean, 3.0f));
+
+    // ---- phase 3: segments in forward order, seconds ----
+    const float *p = ws.edge_p + m.edge_off;
+    int32_t *out_idx = res.ph_idx_seq + m.seg_off;
+    int32_t *out_t = res.ph_time_int + m.seg_off;
+    double *out_iv = res.intervals + 2 * m.seg_off;
+    for (int k = lane; k < n_seg; k += 32) {
+        const int tk = rev_t[n_seg - 1 - k];
+        out_idx[k] = rev_idx[n_seg - 1 - k];
+        out_t[k] = tk;
+        out_iv[2 * k] = seg_time(p, tk, T, frame_length);
+        out_iv[2 * k + 1] = (k + 1 < n_seg) ? seg_time(p, rev_t[n_seg - 2 - k], T, frame_length)
+                                            : __dmul_rn(frame_length, (double)T);
+    }
+    if (lane == 0) {
+        res.status[u] = (final_score == HFA_NEG_INF) ? 4 : 0;
+        res.n_seg[u] = n_seg;
+        res.end_state[u] = s_end;
+        res.final_score[u] = final_score;
+        res.total_conf[u] = total;
+    }
+}
+
+// test helper: unpack one utterance's backpointers to int8 [T][S] (row 0 = -1, :247)
+__global__ void hfa_unpack_bp_kernel(HfaWs ws, int u, int8_t *__restrict__ out)
+{
+    const HfaUtt m = ws.utt[u];
+    const int64_t n = (int64_t)m.T * m.S;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / m.S), s = (int)(i - (int64_t)t * m.S);
+        const uint32_t w = ws.bp[m.bp_off + (int64_t)(t >> 4) * m.Sp + s];
+        const int b = t & 15;
+        const int code = ((w >> (16 + b)) & 1u) ? 2 : (int)((w >> b) & 1u);
+        out[i] = (int8_t)((t == 0) ? -1 : code);
+    }
+}
+
+}  // namespace
+
+cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
+                                 const HfaResultPtrs &res, float *frame_conf, float *dp_path)
+{
+    if (n <= 0) return cudaSuccess;
+    const int blocks = (n + HFA_BT_WARPS - 1) / HFA_BT_WARPS;
+    hfa_backtrace_kernel<<<blocks, HFA_BT_WARPS * 32, 0, c.stream>>>(c.ws, order, n, res, frame_conf,
+                                                                    dp_path, c.frame_length);
+    return cudaGetLastError();
+}
+
+cudaError_t hfa_launch_unpack_bp(const HfaLaunchCtx &c, int utt, int8_t *out)
+{
+    hfa_unpack_bp_kernel<<<148, 256, 0, c.stream>>>(c.ws, utt, out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,142 @@
+// hfa_common.cuh -- shared declarations of the sm_100a forced-alignment kernels.
+//
+// Data layout in HBM (one "plan" = one ragged batch, see hfa_plan.cu):
+//   emissions  emis[utt][t][s]  f32, row stride Sp = round_up(S, 4) so every row and every 16-frame
+//              tile starts 16-byte aligned -> a tile is ONE contiguous 1-D bulk (TMA) copy.
+//              Columns S..Sp-1 hold -inf (inert pad states to the right of the last real state).
+//   edge pair  edge2[utt][t]    {log(edge_prob+1e-6), log(1-edge_prob+1e-6)} f32x2, frame count
+//              padded to a multiple of 16 per utterance so every tile copy is 128 bytes.
+//   edge_p     edge_p[utt][t]   f32 clamp((sigmoid-0.1)/0.8) (same padded indexing as edge2).
+//   backptr    bp[utt][t/16][s] u32: bit tt = "advanced by one" and bit 16+tt = "jumped over an
+//              SP" for frame t = 16*(t/16)+tt  (2 bits per DP cell, written once per 16 frames).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define HFA_TILE_T 16            // frames per emission tile == frames per backpointer word
+#define HFA_WARP_MAX_K 8         // states per lane in the warp-per-utterance kernel
+#define HFA_WARP_MAX_S (32 * HFA_WARP_MAX_K)
+#define HFA_CTA_K 8              // states per thread in the CTA-per-utterance kernel
+#define HFA_NUM_CLASSES 8        // K = 1..8 for the warp kernel (index K-1); class 8 -> CTA kernel
+
+struct HfaUtt {                  // 64 bytes, one per utterance, device copy lives in the workspace
+    int32_t T, S, Sp, status;
+    int64_t seg_off;             // into ids / per-segment outputs (ints)
+    int64_t emis_off;            // floats, multiple of 4
+    int64_t edge_off;            // frames, multiple of 16 (edge2 / edge_p index)
+    int64_t bp_off;              // u32 words
+    int64_t frame_off;           // frames, unpadded (frame_conf / dp_path / path_state / dense in)
+    int64_t cell_off;            // sum of T*S of the previous utterances (dense ragged dumps)
+};
+static_assert(sizeof(HfaUtt) == 64, "HfaUtt must stay 64 bytes");
+
+struct HfaInput {                // per-utterance logits descriptor (changes per call)
+    const void *frame;
+    const void *edge;
+    int64_t frame_st, frame_sv, edge_st;
+};
+
+// device-side view of the workspace (pointers computed on the host from the plan's layout)
+struct HfaWs {
+    const HfaUtt *utt;
+    const int32_t *ids;          // concatenated phoneme ids
+    const int32_t *order;        // bucket order lists (see plan)
+    const int32_t *row_blocks;   // exclusive prefix of emission row-blocks per utterance [n+1]
+    HfaInput *inputs;
+    float *emis;
+    float2 *edge2;
+    float *edge_p;
+    uint32_t *bp;
+    int32_t *path_state;         // [sum T]
+    int32_t *rev_idx;            // [sum S] segments in backward order
+    int32_t *rev_t;              // [sum S]
+    float *dp_last;              // end-of-forward scores: [n_utt][2] = dp[T-1][S-1], dp[T-1][S-2]
+};
+
+#define HFA_NEG_INF __uint_as_float(0xff800000u)
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hfa_smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void hfa_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hfa_smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void hfa_fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void hfa_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hfa_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void hfa_bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                              uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(hfa_smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(hfa_smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(hfa_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void hfa_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!hfa_mbar_try_wait(bar, parity)) {
+    }
+}
+
+// the one mixed-precision operation of the recurrence (alignment_decoder.py:182-187):
+// f32( f64(a) + f64(curr) * ratio ), multiply and add rounded separately (no FMA contraction).
+__device__ __forceinline__ float hfa_advance(float a, float curr, double ratio)
+{
+    return __double2float_rn(__dadd_rn((double)a, __dmul_rn((double)curr, ratio)));
+}
+
+template <typename T> __device__ __forceinline__ float hfa_to_float(T v);
+template <> __device__ __forceinline__ float hfa_to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float hfa_to_float<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float hfa_to_float<__nv_bfloat16>(__nv_bfloat16 v)
+{
+    return __bfloat162float(v);
+}
+
+// typed views of the caller's result blob (layout: HfaResultLayout in include/hfa_align.h)
+struct HfaResultPtrs {
+    int32_t *status, *n_seg, *end_state;
+    float *final_score, *total_conf;
+    int32_t *ph_idx_seq, *ph_time_int;
+    double *intervals;
+};
+
+// host-side launchers implemented in the .cu files (all enqueue on `stream`, return cudaError_t)
+struct HfaLaunchCtx {
+    HfaWs ws;
+    int32_t n_utt;
+    int32_t vocab;
+    double frame_length;
+    cudaStream_t stream;
+};

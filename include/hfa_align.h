@@ -1,0 +1,151 @@
+/*
+ * hfa_align.h -- C ABI of libhfa_align.so, the B200 (sm_100a) forced-alignment decoder.
+ *
+ * This is the drop-in boundary for ONE path of yjzxkxdn/HubertFA: tools/alignment_decoder.py
+ * (AlignmentDecoder.decode :26-143, ._decode :232-294, .forward_pass :170-230).  The reference
+ * has no FFI of its own (it is pure Python + numba), so each entry point below names the
+ * reference lines it replaces; INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked [dev] is device memory owned by the caller, [host]
+ *     is host memory owned by the caller.  The library never allocates device memory and never
+ *     synchronises the stream; kernels are enqueued on the cudaStream_t passed as void*.
+ *   - every function returns HFA_OK (0) or a negative HFA_ERR_* code and never throws;
+ *     hfa_last_error() returns a thread-local message for the last failure.
+ *   - a batch is ragged: utterance b has T[b] frames and S[b] phoneme states.  Per-frame arrays
+ *     are indexed through hfa_plan_frame_offsets(), per-state / per-segment arrays through
+ *     hfa_plan_seg_offsets() (both [n_utt + 1], host, int64).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef HFA_ALIGN_H
+#define HFA_ALIGN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFA_ABI_VERSION 1
+
+enum {
+    HFA_OK = 0,
+    HFA_ERR_ARG = -1,         /* bad argument (null pointer, negative size, ...)                  */
+    HFA_ERR_CUDA = -2,        /* a CUDA runtime call failed; see hfa_last_error()                 */
+    HFA_ERR_UNSUPPORTED = -3, /* shape outside what the kernels cover (S > HFA_MAX_STATES)        */
+    HFA_ERR_NOMEM = -4        /* host allocation for the plan failed                              */
+};
+
+/* per-utterance status codes written to the result blob (mirror the reference's exceptions) */
+enum {
+    HFA_UTT_OK = 0,
+    HFA_UTT_EMPTY = 1,       /* T < 1: reference raises IndexError at alignment_decoder.py:250     */
+    HFA_UTT_BAD_ID = 2,      /* phoneme id outside [0, V): reference raises IndexError at :38/:239 */
+    HFA_UTT_NO_STATES = 3,   /* S < 1: reference raises IndexError at :250                         */
+    HFA_UTT_INFEASIBLE = 4,  /* best path has score -inf (T too short); outputs still follow the
+                                reference (single segment, NaN confidence), flagged for callers    */
+    HFA_UTT_TOO_MANY_STATES = 5 /* S > HFA_MAX_STATES: not covered by the kernels yet              */
+};
+
+/* element type of the logits handed to hfa_emission (the reference applies .float(), :57,:63,:69) */
+enum { HFA_DTYPE_F32 = 0, HFA_DTYPE_F16 = 1, HFA_DTYPE_BF16 = 2 };
+
+#define HFA_MAX_STATES 8192 /* one CTA of 1024 threads x 8 states; larger S -> HFA_ERR_UNSUPPORTED */
+
+typedef struct hfa_plan hfa_plan; /* opaque, host side: collation + bucketing of one ragged batch */
+
+/* Where each result lives inside the result blob (byte offsets from its start).  The blob is one
+ * contiguous device buffer so that a single D2H copy returns everything the host needs. */
+typedef struct HfaResultLayout {
+    int64_t total_bytes;
+    int64_t status;       /* int32 [n_utt]            HFA_UTT_*                                    */
+    int64_t n_seg;        /* int32 [n_utt]            K = number of segments on the best path      */
+    int64_t end_state;    /* int32 [n_utt]            state chosen at T-1 (:269-272)               */
+    int64_t final_score;  /* float [n_utt]            dp[T-1, end_state]                           */
+    int64_t total_conf;   /* float [n_utt]            :97                                          */
+    int64_t ph_idx_seq;   /* int32 [sum S]            :278, utterance b at seg_off[b], K entries   */
+    int64_t ph_time_int;  /* int32 [sum S]            :279                                         */
+    int64_t intervals;    /* double[sum S][2]         :104-113 seconds, before SP filter / clip    */
+} HfaResultLayout;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int hfa_abi_version(void);
+const char *hfa_last_error(void);
+
+/* ---- collation (host only; replaces the reference's one-utterance-per-call loop, infer.py:60) */
+/* T, S: [n_utt] host.  ph_ids: concatenated phoneme ids of all utterances, [sum S] host
+ * (alignment_decoder.py:35).  frame_length = hop_length / sample_rate (:12).
+ * Utterances are bucketed by the number of states per lane (S class) and ordered by T inside a
+ * bucket; invalid utterances get a per-utterance status and are skipped by the kernels. */
+int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const int32_t *S,
+                    const int32_t *ph_ids, double frame_length, hfa_plan **out);
+void hfa_plan_destroy(hfa_plan *plan);
+
+int64_t hfa_plan_workspace_bytes(const hfa_plan *plan); /* device scratch the caller must provide */
+int64_t hfa_plan_total_frames(const hfa_plan *plan);    /* sum T over valid utterances            */
+int64_t hfa_plan_total_states(const hfa_plan *plan);    /* sum S (all utterances)                 */
+int64_t hfa_plan_total_cells(const hfa_plan *plan);     /* sum T*S over valid utterances          */
+const int64_t *hfa_plan_frame_offsets(const hfa_plan *plan); /* [n_utt+1] host                    */
+const int64_t *hfa_plan_seg_offsets(const hfa_plan *plan);   /* [n_utt+1] host                    */
+int hfa_plan_result_layout(const hfa_plan *plan, HfaResultLayout *out);
+/* algorithmic HBM bytes of each kernel for this batch (DESIGN.md "roofline"): [0] emission,
+ * [1] DP forward, [2] backtrace+finalize */
+int hfa_plan_algorithmic_bytes(const hfa_plan *plan, int32_t dtype, int64_t out[3]);
+
+/* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace.
+ * Must be enqueued once per (plan, workspace) before any compute call. */
+int hfa_plan_upload(const hfa_plan *plan, void *workspace /*[dev]*/, void *stream);
+
+/* ---- stage 1: logits -> emissions (alignment_decoder.py:35-40,53-71,83-84,239,241-242) ------- */
+/* hfa_set_inputs: frame_ptrs[b] -> logits of utterance b addressed as
+ * base[t*frame_stride_t[b] + v*frame_stride_v[b]] (elements; the reference receives strided views of
+ * the [1,T,V+2] head output, networks/task/forced_alignment.py:288-291); edge_ptrs[b][t*edge_stride[b]].
+ * The tables are [host] arrays of [dev] pointers; this call copies them into the workspace (a
+ * pageable-memory H2D copy, so it is NOT capturable into a CUDA graph; every other compute entry
+ * point only launches kernels and is). */
+int hfa_set_inputs(const hfa_plan *plan, void *workspace, const void *const *frame_ptrs,
+                   const int64_t *frame_stride_t, const int64_t *frame_stride_v,
+                   const void *const *edge_ptrs, const int64_t *edge_stride, void *stream);
+int hfa_emission(const hfa_plan *plan, void *workspace, int32_t dtype, void *stream);
+
+/* ---- stage 1': the reference's forward_pass inputs, given directly (parity tests) ----------- */
+/* prob_log: ragged dense [T_b][S_b] f32 blocks concatenated in utterance order (:239);
+ * edge_log / not_edge_log: f32 [sum T] (:241-242); edge_pred: f32 [sum T] (:68-71) or NULL
+ * (NULL -> boundaries are not refined, i.e. edge_diff == 0).  All [dev]. */
+int hfa_pack_emissions(const hfa_plan *plan, void *workspace, const float *prob_log,
+                       const float *edge_log, const float *not_edge_log, const float *edge_pred,
+                       void *stream);
+
+/* ---- stage 2: the stay/advance/skip recurrence (alignment_decoder.py:170-230,245-257) -------- */
+/* dp_dump: NULL, or [dev] f32 [sum T*S] receiving every dp cell (ragged dense, for tests).      */
+int hfa_viterbi_forward(const hfa_plan *plan, void *workspace, float *dp_dump, void *stream);
+
+/* ---- stage 3: end state, backtrace, confidence, intervals (:264-288,:97,:104-113) ----------- */
+/* result: [dev] blob of hfa_plan_result_layout().total_bytes.  frame_conf / dp_path: NULL or
+ * [dev] f32 [sum T] (frame_confidence :284-288 and dp along the path :276). */
+int hfa_backtrace(const hfa_plan *plan, void *workspace, void *result, float *frame_conf,
+                  float *dp_path, void *stream);
+
+/* ---- all stages, logits -> result blob (what AlignmentDecoder.decode_batch calls) ----------- */
+/* = hfa_emission + hfa_viterbi_forward + hfa_backtrace on the inputs of the last hfa_set_inputs. */
+int hfa_align_batch(const hfa_plan *plan, void *workspace, int32_t dtype, void *result,
+                    float *frame_conf, void *stream);
+
+/* ---- introspection for tests: unpacked backpointers of one utterance ------------------------ */
+/* out: [dev] int8 [T_b][S_b], codes 0/1/2 (row 0 is -1 like the reference, :247). */
+int hfa_debug_unpack_backptr(const hfa_plan *plan, const void *workspace, int32_t utt, int8_t *out,
+                             void *stream);
+
+/* byte offset of a workspace region (tests peek at intermediate buffers through this):
+ * which = 0 emissions f32 [sum T*Sp] (Sp = S rounded up to 4), 1 edge pairs f32x2 (per utterance
+ * padded to a multiple of 16 frames), 2 edge_pred f32 (same padding), 3 backpointer words.
+ * Returns -1 for an unknown region. */
+int64_t hfa_plan_debug_region(const hfa_plan *plan, int32_t which, int64_t *n_bytes);
+
+/* number of kernel launches the library has enqueued since load (bench.py's gpu_launches) */
+int64_t hfa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFA_ALIGN_H */

@@ -1,0 +1,109 @@
+"""GPU, tier 1: identical emissions in -> bit-identical DP cells, backpointers, paths and path
+scores out, against the C oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from gpu_util import bits, check_core_against_oracle, run_core_gpu, synth_core_inputs
+from oracle import c_oracle as oc
+from oracle import hfa_oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_cases_one_batch(golden):
+    """All golden cases in ONE ragged batch: every state class incl. the CTA kernel, T=1, S=1,
+    infeasible alignments.  Paths must equal the reference's, scores the oracle's bit for bit."""
+    import torch
+    cs = [golden.case(n) for n in golden.names]
+    els, nes, ps = [], [], []
+    for c in cs:
+        el, ne = oc.edge_logs(c["edge_prob"])
+        els.append(el)
+        nes.append(ne)
+        T = c["prob_log"].shape[0]
+        ps.append(onp.edge_pred(torch.from_numpy(c["edge"][:T])[None]))
+    fl = 512 / 44100
+    out = run_core_gpu([c["ids"] for c in cs], [c["prob_log"] for c in cs], els, nes, ps, fl)
+    for c, g, el, ne, p in zip(cs, out, els, nes, ps):
+        assert np.array_equal(g["ph_idx_seq"], c["ph_idx_seq"]), c["meta"]["name"]
+        assert np.array_equal(g["ph_time_int"], c["ph_time_int"]), c["meta"]["name"]
+        check_core_against_oracle(c["ids"], c["prob_log"], el, ne, g, p, fl)
+        fin = np.isfinite(c["frame_confidence"])
+        np.testing.assert_allclose(g["frame_conf"][fin], c["frame_confidence"][fin], rtol=3e-6)
+
+
+SHAPES = [  # (T, S, style) -- every K class of the warp kernel, tile-boundary T, the CTA kernel
+    (1, 1, "dictionary"), (2, 2, "dictionary"), (15, 5, "alternate"), (16, 9, "alternate"),
+    (17, 12, "dictionary"), (31, 31, "alternate"), (32, 32, "alternate"), (33, 33, "alternate"),
+    (100, 20, "dictionary"), (257, 64, "dictionary"), (300, 65, "dictionary"), (480, 96, "nosp"),
+    (333, 97, "dictionary"), (500, 128, "dictionary"), (512, 129, "dictionary"), (700, 160, "dictionary"),
+    (640, 161, "dictionary"), (650, 192, "dictionary"), (600, 200, "alternate"), (800, 224, "dictionary"),
+    (801, 225, "dictionary"), (900, 256, "dictionary"), (600, 257, "alternate"), (700, 300, "alternate"),
+    (1000, 513, "alternate"), (1300, 1030, "alternate"), (40, 7, "nosp"), (3, 7, "alternate"), (2, 5, "nosp"),
+]
+
+
+def test_random_shapes_all_classes():
+    ins = [synth_core_inputs(T, S, 63, 4000 + i, style, planted=bool(i % 2))
+           for i, (T, S, style) in enumerate(SHAPES)]
+    out = run_core_gpu([x["ids"] for x in ins], [x["prob_log"] for x in ins], [x["el"] for x in ins],
+                       [x["ne"] for x in ins], [x["p"] for x in ins], 0.02)
+    for x, g, shp in zip(ins, out, SHAPES):
+        try:
+            check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], g, x["p"], 0.02)
+        except AssertionError as e:
+            raise AssertionError(f"shape {shp}: {e}") from e
+
+
+def test_ties_go_to_the_earlier_candidate():
+    """Constant emissions and edge logs make stay/advance/skip tie everywhere: the strict '>' scan
+    (alignment_decoder.py:210-218) must be reproduced exactly."""
+    T, S = 64, 21
+    ids = np.array([0, 3, 0, 4, 5, 0, 6, 0, 7, 8, 0, 9, 0, 1, 0, 2, 0, 3, 4, 0, 0][:S], dtype=np.int32)
+    cases = []
+    for val, e, n in [(-1.0, -0.5, -0.5), (0.0, 0.0, 0.0), (-2.0, -1.0, -3.0)]:
+        cases.append((ids, np.full((T, S), val, np.float32), np.full(T, e, np.float32), np.full(T, n, np.float32)))
+    out = run_core_gpu([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], [c[3] for c in cases])
+    for c, g in zip(cases, out):
+        check_core_against_oracle(c[0], c[1], c[2], c[3], g)
+
+
+def test_minus_inf_emissions_do_not_create_nan():
+    T, S = 40, 9
+    x = synth_core_inputs(T, S, 39, 77, "alternate")
+    pl = x["prob_log"].copy()
+    pl[5:9, 3] = -np.inf
+    pl[20, :] = -np.inf
+    out = run_core_gpu([x["ids"]], [pl], [x["el"]], [x["ne"]])
+    check_core_against_oracle(x["ids"], pl, x["el"], x["ne"], out[0])
+
+
+def test_invalid_utterances_get_a_status():
+    import torch
+    from hubertfa_b200 import ops
+    good = synth_core_inputs(50, 9, 39, 5, "alternate")
+    ids_bad = good["ids"].copy()
+    ids_bad[2] = 1000
+    plan = ops.AlignPlan([50, 0, 50], [9, 3, 9], np.concatenate([good["ids"], [0, 1, 0], ids_bad]), 39, 0.02)
+    dev = torch.device("cuda")
+    ws, res = plan.new_workspace(dev), plan.new_result(dev)
+    plan.upload(ws)
+    cat = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)).to(dev)
+    ops.pack_emissions(ws, plan.handle, cat(good["prob_log"]), cat(good["el"]), cat(good["ne"]), None)
+    ops.viterbi_forward(ws, plan.handle, None)
+    ops.backtrace(ws, plan.handle, res, None, None)
+    torch.cuda.synchronize()
+    v = plan.views(res.cpu().numpy())
+    assert list(v["status"]) == [0, 1, 2]
+    assert v["n_seg"][1] == 0 and v["n_seg"][2] == 0
+    r = oc.decode(good["ids"], good["prob_log"], good["el"], good["ne"])
+    assert np.array_equal(v["ph_idx_seq"][:v["n_seg"][0]], r["ph_idx_seq"])
+
+
+def test_long_form_c3_stress():
+    """BASELINE config 3: one 10-minute utterance, T=30000, S=2000 (CTA kernel, 1875 word rows)."""
+    x = synth_core_inputs(30000, 2000, 63, 31337, "dictionary", planted=True)
+    out = run_core_gpu([x["ids"]], [x["prob_log"]], [x["el"]], [x["ne"]], [x["p"]], dump=False)
+    r = check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], out[0], x["p"], full=False)
+    assert len(r["ph_idx_seq"]) > 1000

@@ -1,0 +1,205 @@
+"""GPU, tier 2: from logits through the drop-in ``AlignmentDecoder``.
+
+The logits -> emission boundary is not bit-defined by the reference (torch's log_softmax / sigmoid
+differ between CPU ISA paths and CUDA), so: emissions are compared element-wise with a tolerance
+stated here, paths must match the reference on the golden set, and for any utterance of the random
+sets whose path differs the oracle is re-run on OUR emissions and must then reproduce OUR path
+exactly (which proves a <=few-ulp near-tie in third-party code, not a DP bug)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names
+from gpu_util import bits, synth_core_inputs
+from hubertfa_b200 import ops, synth
+from hubertfa_b200.alignment_decoder import AlignmentDecoder
+from oracle import c_oracle as oc
+from oracle import hfa_oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+EMIS_ATOL = 4e-6      # |log-softmax| values are O(1..20): a few f32 ulps of the max / log-sum terms
+EDGE_ATOL = 2e-6      # on edge_log / not_edge_log away from the clamp (see test)
+
+
+def _emission_gpu(frames, edges, ids_list, V):
+    """Runs only the emission kernel; returns per-utterance (emis [T,S], edge2 [T,2], edge_p [T])."""
+    dev = torch.device("cuda")
+    T = [f.shape[0] for f in frames]
+    S = [len(i) for i in ids_list]
+    plan = ops.AlignPlan(T, S, np.concatenate(ids_list), V, 0.02)
+    ws = plan.new_workspace(dev)
+    plan.upload(ws)
+    plan.set_inputs(ws, [f.data_ptr() for f in frames], [f.stride(0) for f in frames],
+                    [f.stride(1) for f in frames], [e.data_ptr() for e in edges], [e.stride(0) for e in edges])
+    ops.emission(ws, plan.handle, ops.TORCH_TO_DTYPE[frames[0].dtype])
+    torch.cuda.synchronize()
+    return plan, ws
+
+
+def _ws_region(plan, ws, name):
+    return plan.debug_region(ws, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("V", [39, 63, 74, 200])
+def test_emission_kernel_vs_oracle_and_torch(dtype, V):
+    """Strided views of a [T, V+2] head output (networks/task/forced_alignment.py:288-291)."""
+    dev = torch.device("cuda")
+    shapes = [(130, 20), (64, 33), (257, 150), (1, 3), (63, 5), (65, 70)]
+    heads, frames, edges, ids_list = [], [], [], []
+    for i, (T, S) in enumerate(shapes):
+        rng = np.random.default_rng(10 * V + i)
+        vocab = synth.make_vocab(V)
+        ph_seq, _, _ = synth.make_ph_seq(rng, S, V, "dictionary")
+        ids_list.append(np.array([vocab["vocab"][p] for p in ph_seq], dtype=np.int32))
+        g = torch.Generator().manual_seed(10 * V + i)
+        head = (3.0 * torch.randn(1, T, V + 2, generator=g)).to(dtype).to(dev)
+        heads.append(head)
+        frames.append(head[0, :, 2:])
+        edges.append(head[0, :, 0])
+    plan, ws = _emission_gpu(frames, edges, ids_list, V)
+    emis = _ws_region(plan, ws, "emis").cpu().numpy()
+    edge2 = _ws_region(plan, ws, "edge2").cpu().numpy()
+    edgep = _ws_region(plan, ws, "edge_p").cpu().numpy()
+    eo = fo = 0
+    for (T, S), head, ids in zip(shapes, heads, ids_list):
+        Sp = (S + 3) // 4 * 4
+        e = emis[eo:eo + T * Sp].reshape(T, Sp)
+        x = head[0].float().cpu()
+        # oracle (libm) and the reference's own torch call on CPU and on CUDA
+        want_c = oc.emission(np.ascontiguousarray(x[:, 2:].numpy()), ids)
+        want_t = onp.frame_log_probs(x[None, :, 2:], ids, V)[:, ids]
+        want_cuda = onp.frame_log_probs(head[:, :, 2:], ids, V)[:, ids]
+        for want in (want_c, want_t, want_cuda):
+            np.testing.assert_allclose(e[:, :S], want, rtol=0, atol=EMIS_ATOL)
+        assert np.isneginf(e[:, S:]).all()
+        p = edgep[fo:fo + T]
+        p_t = onp.edge_pred(x[None, :, 0])
+        np.testing.assert_allclose(p, p_t, rtol=0, atol=2.5e-7)
+        _, ep = onp.edge_streams(p)                      # exact from OUR p: isolates the f64 log
+        el, ne = onp.edge_logs(ep)
+        got = edge2[fo:fo + T]
+        np.testing.assert_allclose(got[:, 0], el, rtol=1e-6, atol=EDGE_ATOL)
+        np.testing.assert_allclose(got[:, 1], ne, rtol=1e-6, atol=EDGE_ATOL)
+        eo += T * Sp
+        fo += (T + 15) // 16 * 16
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_decode_matches_reference_golden(golden, name):
+    c = golden.case(name)
+    m = c["meta"]
+    dec = AlignmentDecoder(synth.make_vocab(m["V"]), {"hop_length": m["hop"], "sample_rate": m["sr"]})
+    frame = torch.from_numpy(c["frame"])[None].cuda()
+    edge = torch.from_numpy(c["edge"])[None].cuda()
+    ctc = torch.zeros(1, frame.shape[1], m["V"]).cuda()
+    ph, ph_iv, wd, wd_iv, conf = dec.decode(frame, edge, ctc, m["wav_length"], m["ph_seq"], m["word_seq"],
+                                            m["ph_idx_to_word_idx"])
+    assert np.array_equal(dec.ph_idx_seq, c["ph_idx_seq"])
+    assert np.array_equal(dec.ph_time_int_pred, c["ph_time_int"])
+    assert list(ph) == list(c["ph_seq_pred"]) and list(wd) == list(c["word_seq_pred"])
+    assert ph_iv.shape == c["ph_intervals_pred"].shape and ph_iv.dtype == np.float64
+    assert wd_iv.shape == c["word_intervals_pred"].shape
+    np.testing.assert_allclose(ph_iv, c["ph_intervals_pred"], rtol=0, atol=1e-7)   # seconds
+    np.testing.assert_allclose(wd_iv, c["word_intervals_pred"], rtol=0, atol=1e-7)
+    assert isinstance(conf, np.float32)
+    if np.isfinite(c["total_confidence"]):
+        np.testing.assert_allclose(conf, c["total_confidence"], rtol=1e-4)
+        fin = np.isfinite(c["frame_confidence"])
+        np.testing.assert_allclose(dec.frame_confidence[fin], c["frame_confidence"][fin], rtol=2e-4, atol=1e-12)
+    else:
+        assert np.isnan(conf)
+    np.testing.assert_allclose(dec.edge_prob, c["edge_prob"], atol=5e-7)
+    assert dec.ph_frame_pred.shape == (c["prob_log"].shape[0], m["V"])
+
+
+def test_decode_batch_c2_sized_vs_oracle():
+    """BASELINE config 2 at full size: 256 utterances, 5-30 s, 20-150 phonemes, V=63."""
+    V = 63
+    T, S = synth.sample_shapes(256, seed=synth.SEED0)
+    vocab, items = synth.make_batch(T, S, V, seed=synth.SEED0, planted=True)
+    mel = synth.MELSPEC_50FPS
+    dec = AlignmentDecoder(vocab, mel)
+    res = dec.decode_batch([it["frame"].cuda() for it in items], [it["edge"].cuda() for it in items],
+                           [it["ph_seq"] for it in items], [it["word_seq"] for it in items],
+                           [it["ph_idx_to_word_idx"] for it in items])
+    assert (res.status == 0).all()
+    n_diff = 0
+    for b, it in enumerate(items):
+        out, ex = onp.decode(vocab, mel, it["frame"], it["edge"], None, None, it["ph_seq"], it["word_seq"],
+                             it["ph_idx_to_word_idx"], full=True)
+        idx, tim, iv = res.segments(b)
+        # size-independent properties of any valid alignment
+        assert tim[0] == 0 and (np.diff(tim) > 0).all() and (np.diff(idx) > 0).all()
+        assert (np.diff(idx) <= 2).all() and idx[-1] >= len(it["ids"]) - 2
+        if not (np.array_equal(idx, ex["ph_idx_seq"]) and np.array_equal(tim, ex["ph_time_int"])):
+            n_diff += 1
+            continue
+        got = res[b]
+        assert list(got[0]) == list(out[0]) and list(got[2]) == list(out[2])
+        np.testing.assert_allclose(got[1], out[1], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(got[3], out[3], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(got[4], out[4], rtol=1e-4)
+    # planted (peaked) logits: near-ties between different paths are rare; all 256 are expected equal
+    assert n_diff == 0, f"{n_diff} of 256 paths differ from the oracle"
+
+
+def test_decode_batch_equals_single_decode_and_packed_input():
+    V = 39
+    T, S = synth.sample_shapes(24, seed=5, min_s=1, max_s=6, s_lo=3, s_hi=60)
+    vocab, items = synth.make_batch(T, S, V, seed=5)
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    frames = [it["frame"].cuda() for it in items]
+    edges = [it["edge"].cuda() for it in items]
+    seqs = [it["ph_seq"] for it in items]
+    res = dec.decode_batch(frames, edges, seqs, [it["word_seq"] for it in items],
+                           [it["ph_idx_to_word_idx"] for it in items], want_frame_confidence=True)
+    packed = dec.decode_batch(torch.cat([f[0] for f in frames]), torch.cat([e[0] for e in edges]), seqs,
+                              [it["word_seq"] for it in items], [it["ph_idx_to_word_idx"] for it in items],
+                              lengths=[int(t) for t in T])
+    for b, it in enumerate(items):
+        one = dec.decode(frames[b], edges[b], it["ctc"].cuda(), None, it["ph_seq"], it["word_seq"],
+                         it["ph_idx_to_word_idx"])
+        for got in (res[b], packed[b]):
+            assert list(got[0]) == list(one[0]) and list(got[2]) == list(one[2])
+            assert np.array_equal(got[1].reshape(one[1].shape), one[1])
+            assert np.array_equal(got[3].reshape(one[3].shape), one[3])
+            assert bits(got[4]) == bits(one[4])
+        f0, f1 = res.frame_off[b], res.frame_off[b + 1]
+        assert np.array_equal(bits(res.frame_confidence[f0:f1]), bits(dec.frame_confidence))
+        assert np.array_equal(dec.ctc(), onp.ctc_greedy(it["ctc"][0].numpy()))
+
+
+def test_random_logits_tier2_protocol():
+    """Unpeaked Gaussian logits (many near-ties): every mismatch must be explained by re-running the
+    oracle DP on our own emissions."""
+    V = 74
+    T, S = synth.sample_shapes(96, seed=99, min_s=2, max_s=12, s_lo=5, s_hi=120)
+    vocab, items = synth.make_batch(T, S, V, seed=99)
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    frames = [it["frame"].cuda()[0] for it in items]
+    edges = [it["edge"].cuda()[0] for it in items]
+    res = dec.decode_batch(frames, edges, [it["ph_seq"] for it in items])
+    plan, ws = _emission_gpu(frames, edges, [it["ids"] for it in items], V)
+    emis = _ws_region(plan, ws, "emis").cpu().numpy()
+    edge2 = _ws_region(plan, ws, "edge2").cpu().numpy()
+    eo = fo = 0
+    differ = 0
+    for b, it in enumerate(items):
+        t, s = int(T[b]), int(S[b])
+        sp = (s + 3) // 4 * 4
+        ours = np.ascontiguousarray(emis[eo:eo + t * sp].reshape(t, sp)[:, :s])
+        el = np.ascontiguousarray(edge2[fo:fo + t, 0])
+        ne = np.ascontiguousarray(edge2[fo:fo + t, 1])
+        eo += t * sp
+        fo += (t + 15) // 16 * 16
+        idx, tim, _ = res.segments(b)
+        r = oc.decode(it["ids"], ours, el, ne)
+        assert np.array_equal(idx, r["ph_idx_seq"]) and np.array_equal(tim, r["ph_time_int"]), \
+            f"utterance {b}: DP on our own emissions does not reproduce our path"
+        ex = onp.decode(vocab, synth.MELSPEC_50FPS, it["frame"], it["edge"], None, None, it["ph_seq"], full=True)[1]
+        if not (np.array_equal(idx, ex["ph_idx_seq"]) and np.array_equal(tim, ex["ph_time_int"])):
+            differ += 1
+    print(f"tier-2: {differ} of {len(items)} paths differ from the CPU-torch reference (all explained)")
+    assert differ <= 3
