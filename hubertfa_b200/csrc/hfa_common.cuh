@@ -105,7 +105,11 @@ __device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity
 }
 __device__ __forceinline__ void hfa_mbar_wait(uint64_t *bar, uint32_t parity)
 {
+    // try_wait suspends the thread for a hardware time slice; a copy that never lands (a bug) must
+    // not hang the GPU, so give up loudly after ~seconds of polling.
+    uint32_t spins = 0;
     while (!hfa_mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
     }
 }
 

@@ -45,9 +45,10 @@ def lib():
         L.hfa_oracle_confidence.restype = C.c_float
         L.hfa_oracle_intervals.argtypes = [C.c_int32, C.c_int32, _i32p, _f32p, C.c_double, _f64p]
         L.hfa_oracle_intervals.restype = None
-        L.hfa_oracle_align_batch.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i64p, _i64p,
-                                             _f32p, _f32p, _i32p, C.c_double, _i32p, _i32p, _i32p,
-                                             _f64p, _f32p, _i32p, C.c_int32]
+        L.hfa_oracle_align_batch.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i64p,
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i32p,
+                                             C.c_double, _i32p, _i32p, _i32p, _f64p, _f32p, _i32p,
+                                             C.c_int32]
         L.hfa_oracle_align_batch.restype = C.c_int
         L.hfa_oracle_max_threads.restype = C.c_int
         _lib = L
@@ -124,24 +125,31 @@ def intervals(T: int, ph_time_int, p, frame_length: float) -> np.ndarray:
 
 
 def align_batch(T, S, V, frame_logits, edge_logits, ph_ids, frame_length, n_threads=0):
-    """Ragged batch through the whole C path.  frame_logits: concatenated dense [T_b][V] blocks,
-    edge_logits: concatenated [T_b], ph_ids: concatenated [S_b].  Returns a dict of ragged outputs."""
+    """Ragged batch through the whole C path (pthread pool over utterances).
+
+    frame_logits: f32 [sum T, V] (any row stride, unit column stride, e.g. head[:, 2:]),
+    edge_logits: f32 [sum T] (any stride, e.g. head[:, 0]), ph_ids: concatenated [sum S]."""
     T = np.ascontiguousarray(T, dtype=np.int32)
     S = np.ascontiguousarray(S, dtype=np.int32)
     B = len(T)
-    edge_off = np.zeros(B, dtype=np.int64)
+    frame_logits = np.asarray(frame_logits)
+    edge_logits = np.asarray(edge_logits)
+    if frame_logits.ndim == 1:
+        frame_logits = frame_logits.reshape(-1, V)
+    assert frame_logits.dtype == np.float32 and edge_logits.dtype == np.float32
+    assert frame_logits.strides[1] == 4 and frame_logits.shape[1] == V
+    row_off = np.zeros(B, dtype=np.int64)
     seg_off = np.zeros(B, dtype=np.int64)
     if B > 1:
-        edge_off[1:] = np.cumsum(T[:-1].astype(np.int64))
+        row_off[1:] = np.cumsum(T[:-1].astype(np.int64))
         seg_off[1:] = np.cumsum(S[:-1].astype(np.int64))
-    logit_off = edge_off * V
     nseg_tot = int(S.astype(np.int64).sum())
     out = dict(n_seg=np.zeros(B, np.int32), ph_idx_seq=np.zeros(nseg_tot, np.int32),
                ph_time_int=np.zeros(nseg_tot, np.int32), intervals=np.zeros(2 * nseg_tot, np.float64),
                total_conf=np.zeros(B, np.float32), status=np.zeros(B, np.int32), seg_off=seg_off)
-    bad = lib().hfa_oracle_align_batch(B, V, T, S, logit_off, edge_off, seg_off,
-                                       np.ascontiguousarray(frame_logits, dtype=np.float32).reshape(-1),
-                                       np.ascontiguousarray(edge_logits, dtype=np.float32).reshape(-1),
+    bad = lib().hfa_oracle_align_batch(B, V, T, S, row_off, seg_off, frame_logits.ctypes.data,
+                                       frame_logits.strides[0] // 4, edge_logits.ctypes.data,
+                                       edge_logits.strides[0] // 4,
                                        np.ascontiguousarray(ph_ids, dtype=np.int32), float(frame_length),
                                        out["n_seg"], out["ph_idx_seq"], out["ph_time_int"],
                                        out["intervals"], out["total_conf"], out["status"], int(n_threads))
