@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -16,6 +17,8 @@
 
 cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
                                float *dp_dump);
+cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
+                                   float *dp_dump);
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp,
                               float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype);
@@ -89,6 +92,7 @@ struct hfa_plan {
     int32_t class_begin[HFA_NUM_CLASSES + 2] = {0};
     int32_t class_count[HFA_NUM_CLASSES + 1] = {0};
     int32_t cta_max_sp = 0, max_sp = 4;
+    int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
     int64_t total_frames = 0, total_states = 0, total_cells = 0, padded_cells = 0;
@@ -243,6 +247,19 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             p->order.insert(p->order.end(), lists[c].begin(), lists[c].end());
             all.insert(all.end(), lists[c].begin(), lists[c].end());
         }
+        // merged warp-kernel list: longest expected run time first (frames x per-frame cost, which
+        // grows with the states per lane)
+        std::vector<int32_t> warp_all;
+        for (int c = 0; c < HFA_NUM_CLASSES; ++c) {
+            warp_all.insert(warp_all.end(), lists[c].begin(), lists[c].end());
+            if (!lists[c].empty()) p->warp_max_k = c + 1;
+        }
+        auto cost = [&](int32_t b) { return (int64_t)p->utt[b].T * (2 + (p->utt[b].Sp + 31) / 32); };
+        std::sort(warp_all.begin(), warp_all.end(),
+                  [&](int32_t a, int32_t b) { return cost(a) != cost(b) ? cost(a) > cost(b) : a < b; });
+        p->warp_all_begin = (int32_t)p->order.size();
+        p->warp_all_count = (int32_t)warp_all.size();
+        p->order.insert(p->order.end(), warp_all.begin(), warp_all.end());
         std::sort(all.begin(), all.end(), by_len);
         p->bt_begin = (int32_t)p->order.size();
         p->order.insert(p->order.end(), all.begin(), all.end());
@@ -408,48 +425,71 @@ int hfa_pack_emissions(const hfa_plan *p, void *workspace, const float *prob_log
     return HFA_OK;
 }
 
+// HFA_DP_MODE=merged (default): every warp-kernel state class in one launch.
+// HFA_DP_MODE=streams: one launch per class, forked onto side streams and joined.
+// HFA_DP_MODE=serial: one launch per class on the caller's stream.
+static int dp_mode()
+{
+    static const int mode = [] {
+        const char *e = std::getenv("HFA_DP_MODE");
+        if (e && std::strcmp(e, "streams") == 0) return 1;
+        if (e && std::strcmp(e, "serial") == 0) return 2;
+        return 0;
+    }();
+    return mode;
+}
+
 int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void *stream)
 {
     if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_viterbi_forward: NULL plan/workspace");
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
-    // The state-count classes are independent launches: fork them onto side streams so that the
-    // serial-in-time tails of the classes overlap instead of adding up, then join (capturable).
-    int n_active = 0;
-    for (int k = 0; k <= HFA_NUM_CLASSES; ++k) n_active += p->class_count[k] > 0;
-    if (n_active == 0) return HFA_OK;
+    const int mode = dp_mode();
+    const int n_cta = p->class_count[HFA_NUM_CLASSES];
+    // launches of this call: (merged ? 1 : one per class) + the CTA-per-utterance kernel
+    struct Item { int k; const int32_t *order; int n; };
+    Item items[HFA_NUM_CLASSES + 2];
+    int n_items = 0;
+    if (mode == 0) {
+        if (p->warp_all_count > 0)
+            items[n_items++] = {0, c.ws.order + p->warp_all_begin, p->warp_all_count};
+    } else {
+        for (int k = 0; k < HFA_NUM_CLASSES; ++k)
+            if (p->class_count[k] > 0)
+                items[n_items++] = {k + 1, c.ws.order + p->class_begin[k], p->class_count[k]};
+    }
+    if (n_cta > 0) items[n_items++] = {-1, c.ws.order + p->class_begin[HFA_NUM_CLASSES], n_cta};
+    if (n_items == 0) return HFA_OK;
+
+    const bool fork = n_items > 1 && mode != 2;
     HfaSideStreams *ss = nullptr;
-    if (n_active > 1) {
+    if (fork) {
         ss = side_streams();
         if (!ss) return fail(HFA_ERR_CUDA, "hfa_viterbi_forward: cannot create side streams");
         cudaError_t e = cudaEventRecord(ss->fork, c.stream);
         if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: fork record");
     }
     const cudaStream_t user = c.stream;
-    int slot = 0;
-    for (int k = 0; k <= HFA_NUM_CLASSES; ++k) {
-        if (p->class_count[k] == 0) continue;
+    for (int it = 0; it < n_items; ++it) {
         cudaError_t e;
-        if (slot > 0) {
-            c.stream = ss->stream[slot - 1];
+        const bool side = fork && it > 0;
+        c.stream = side ? ss->stream[it - 1] : user;
+        if (side) {
             e = cudaStreamWaitEvent(c.stream, ss->fork, 0);
             if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: fork wait");
-        } else {
-            c.stream = user;
         }
-        if (k < HFA_NUM_CLASSES)
-            e = hfa_launch_dp_warp(c, k + 1, c.ws.order + p->class_begin[k], p->class_count[k],
-                                   dp_dump);
+        if (items[it].k == 0)
+            e = hfa_launch_dp_warp_any(c, p->warp_max_k, items[it].order, items[it].n, dp_dump);
+        else if (items[it].k > 0)
+            e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
         else
-            e = hfa_launch_dp_cta(c, c.ws.order + p->class_begin[k], p->class_count[k],
-                                  p->cta_max_sp, dp_dump);
+            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->cta_max_sp, dp_dump);
         if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: kernel launch");
         g_launches += 1;
-        if (slot > 0) {
-            e = cudaEventRecord(ss->join[slot - 1], c.stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ss->join[slot - 1], 0);
+        if (side) {
+            e = cudaEventRecord(ss->join[it - 1], c.stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ss->join[it - 1], 0);
             if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: join");
         }
-        ++slot;
     }
     return HFA_OK;
 }

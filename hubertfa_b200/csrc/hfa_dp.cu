@@ -13,8 +13,8 @@
 //   hfa_dp_warp_kernel<K>  S <= 32*K <= 256: ONE WARP per utterance, K consecutive states per lane
 //       held in registers (dp, curr, backpointer bits); per frame only the last two advance scores
 //       of the left neighbour lane cross lanes (2 warp shuffles).  Emission rows are streamed
-//       HBM -> smem by the TMA engine as contiguous 16-frame tiles (1-D bulk copy + mbarrier,
-//       double buffered); backpointers leave as one bit-packed u32 per state per 16 frames.
+//       HBM -> smem by the TMA engine as contiguous 8-frame tiles (1-D bulk copy + mbarrier,
+//       3 stages); backpointers leave as one bit-packed u32 per state per 16 frames.
 //   hfa_dp_cta_kernel      S <= 8192: ONE CTA per utterance, 8 states per thread, the two boundary
 //       scores cross warps through shared memory with one __syncthreads per frame.
 //
@@ -25,28 +25,43 @@
 namespace {
 
 // one frame of the recurrence for the K states owned by this lane/thread.
-// up1 / up2: advance scores of states (first-1) and (first-2), already -inf where they do not exist.
+// up1 / up2: advance scores of states (first-1) and (first-2) (up1 already -inf where that state
+// does not exist).  sp_and[k] = 0 for id-0 (SP) states else ~0 (curr is zeroed by an AND, :226-228);
+// jump_cap[k] = +inf where state first+k may be entered by a two-state jump, else -inf (:191-202).
 template <int K>
 __device__ __forceinline__ void hfa_select(const float (&e)[K], const float (&stay)[K],
                                            const float (&adv)[K], float up1, float up2,
-                                           uint32_t sp_mask, uint32_t skip_mask, uint32_t m1,
-                                           uint32_t m2, float (&dp)[K], float (&cu)[K],
+                                           const uint32_t (&sp_and)[K], const float (&jump_cap)[K],
+                                           uint32_t m1, uint32_t m2, float (&dp)[K], float (&cu)[K],
                                            uint32_t (&bits)[K])
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float p2 = (k == 0) ? up1 : adv[k - 1];
         const float p3 = (k == 0) ? up2 : ((k == 1) ? up1 : adv[k - 2]);
-        const bool g1 = p2 > stay[k];
-        const float m = g1 ? p2 : stay[k];
-        const bool g2 = ((skip_mask >> k) & 1u) && (p3 > m);
-        dp[k] = g2 ? p3 : m;
-        if (g1) bits[k] |= m1;
-        if (g2) bits[k] |= m2;
-        const float held = fmaxf(cu[k], e[k]);
-        float c = (g1 || g2) ? e[k] : held;
-        if ((sp_mask >> k) & 1u) c = 0.0f;
-        cu[k] = c;
+        // Written as PTX so that the two backpointer bits become predicated ORs and the selects
+        // stay selects.  Semantics (alignment_decoder.py:210-228): strict '>' scanned in the order
+        // stay, +1, +2 (ties keep the earlier candidate); curr = moved ? e : max(curr, e); curr of
+        // an id-0 state is 0 (AND with 0); a two-state jump is only a candidate where jump_cap is
+        // +inf (min with -inf removes it).
+        asm("{\n\t"
+            ".reg .pred q1, q2, q3;\n\t"
+            ".reg .f32 m, j, h;\n\t"
+            "min.f32 j, %5, %6;\n\t"
+            "setp.gt.f32 q1, %3, %4;\n\t"
+            "selp.f32 m, %3, %4, q1;\n\t"
+            "setp.gt.f32 q2, j, m;\n\t"
+            "selp.f32 %0, j, m, q2;\n\t"
+            "@q1 or.b32 %2, %2, %9;\n\t"
+            "@q2 or.b32 %2, %2, %10;\n\t"
+            "max.f32 h, %1, %7;\n\t"
+            "or.pred q3, q1, q2;\n\t"
+            "selp.f32 h, %7, h, q3;\n\t"
+            "and.b32 %1, h, %8;\n\t"
+            "}"
+            : "=f"(dp[k]), "+f"(cu[k]), "+r"(bits[k])
+            : "f"(p2), "f"(stay[k]), "f"(p3), "f"(jump_cap[k]), "f"(e[k]), "r"(sp_and[k]), "r"(m1),
+              "r"(m2));
     }
 }
 
@@ -96,70 +111,108 @@ __device__ __forceinline__ void hfa_store_bits(uint32_t *dst, const uint32_t (&b
     }
 }
 
-// per-thread static state flags (alignment_decoder.py:194,227): bit k set when state first+k is an
-// id-0 (SP) state / when state first+k may be entered by a two-state jump (i >= 2, ids[i-1] == 0)
+// per-thread static state flags (alignment_decoder.py:194,227)
 template <int K>
 __device__ __forceinline__ void hfa_state_masks(const int32_t *ids, int first, int S,
-                                                uint32_t &sp_mask, uint32_t &skip_mask)
+                                                uint32_t (&sp_and)[K], float (&jump_cap)[K])
 {
-    sp_mask = 0;
-    skip_mask = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int i = first + k;
+        sp_and[k] = 0xffffffffu;
+        jump_cap[k] = HFA_NEG_INF;
         if (i < S) {
-            if (ids[i] == 0) sp_mask |= 1u << k;
-            if (i >= 2 && ids[i - 1] == 0) skip_mask |= 1u << k;
+            if (ids[i] == 0) sp_and[k] = 0u;
+            if (i >= 2 && ids[i - 1] == 0) jump_cap[k] = __uint_as_float(0x7f800000u);
         }
     }
+}
+
+// shared-memory loads by 32-bit shared address (keeps generic->shared address arithmetic out of
+// the per-frame loop)
+template <int K> __device__ __forceinline__ void hfa_lds_row(uint32_t addr, float (&e)[K])
+{
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(e[4 * q]), "=f"(e[4 * q + 1]), "=f"(e[4 * q + 2]), "=f"(e[4 * q + 3])
+                         : "r"(addr + 16u * q));
+    } else if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < K / 2; ++q)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(e[2 * q]), "=f"(e[2 * q + 1])
+                         : "r"(addr + 8u * q));
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e[k]) : "r"(addr + 4u * k));
+    }
+}
+__device__ __forceinline__ float2 hfa_lds_f2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
 // warp per utterance
 // ---------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(32)
-hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restrict__ dp_dump)
+constexpr int HFA_WARP_TILE = 8;      // frames per TMA stage (two stages = one backpointer word)
+constexpr int HFA_WARP_STAGES = 3;    // the copy of tile i+3 is issued when tile i has been consumed
+
+template <int K> constexpr size_t hfa_warp_smem_bytes()
 {
+    // [stages x 8 rows x 32K floats][one slack row: the prefetch of "row 8" of the last stage]
+    // [stages x 8 edge pairs][one slack pair][stages mbarriers]
+    return (size_t)(HFA_WARP_STAGES * HFA_WARP_TILE + 1) * 32 * K * sizeof(float) +
+           (size_t)(HFA_WARP_STAGES * HFA_WARP_TILE + 1) * sizeof(float2) +
+           HFA_WARP_STAGES * sizeof(uint64_t);
+}
+
+template <int K, bool DUMP>
+__device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
+                                                 float *__restrict__ dp_dump,
+                                                 unsigned char *smem_raw)
+{
+    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
     constexpr int ROW_MAX = 32 * K;                       // floats per smem tile row (upper bound)
-    constexpr int TILE_FLOATS = HFA_TILE_T * ROW_MAX;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TILE_FLOATS = TT * ROW_MAX;
     float *tile0 = reinterpret_cast<float *>(smem_raw);
-    float2 *edge0 = reinterpret_cast<float2 *>(smem_raw + 2 * TILE_FLOATS * sizeof(float));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * TILE_FLOATS * sizeof(float) +
-                                                 2 * HFA_TILE_T * sizeof(float2));
+    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + ROW_MAX);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
 
     const int lane = threadIdx.x;
-    const int u = order[blockIdx.x];
     const HfaUtt m = ws.utt[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int first = lane * K;
-    const int n_tiles = (T + HFA_TILE_T - 1) / HFA_TILE_T;
+    const int n_tiles = (T + TT - 1) / TT;
     const float *g_emis = ws.emis + m.emis_off;
     const float2 *g_edge = ws.edge2 + m.edge_off;
     uint32_t *g_bp = ws.bp + m.bp_off;
     const double ratio = __ddiv_rn((double)T, (double)S);     // T / S (:186)
 
     auto issue = [&](int i) {                                  // lane 0 only
-        const int st = i & 1;
-        const int t0 = i * HFA_TILE_T;
-        const int rows = min(HFA_TILE_T, T - t0);
+        const int st = i % NST;
+        const int t0 = i * TT;
+        const int rows = min(TT, T - t0);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)Sp * 4u;
-        hfa_mbar_expect_tx(&bar[st], bytes + HFA_TILE_T * (uint32_t)sizeof(float2));
+        hfa_mbar_expect_tx(&bar[st], bytes + TT * (uint32_t)sizeof(float2));
         hfa_bulk_load(tile0 + st * TILE_FLOATS, g_emis + (int64_t)t0 * Sp, bytes, &bar[st]);
-        hfa_bulk_load(edge0 + st * HFA_TILE_T, g_edge + t0, HFA_TILE_T * (uint32_t)sizeof(float2),
-                      &bar[st]);
+        hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
     };
 
     if (lane == 0) {
-        hfa_mbar_init(&bar[0], 1);
-        hfa_mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
         hfa_fence_mbar_init();
-        issue(0);
-        if (n_tiles > 1) issue(1);
+        for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
     }
-    uint32_t sp_mask, skip_mask;
-    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_mask, skip_mask);
+    uint32_t sp_and[K];
+    float jump_cap[K];
+    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
     const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
     __syncwarp();
 
@@ -169,60 +222,89 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
     for (int k = 0; k < K; ++k) {
         dp[k] = HFA_NEG_INF;
         cu[k] = HFA_NEG_INF;
+        bits[k] = 0;
     }
+    const uint32_t tile_sa = hfa_smem_u32(tile0) + (uint32_t)first * 4u;
+    const uint32_t edge_sa = hfa_smem_u32(edge0);
+    const uint32_t row_bytes = (uint32_t)Sp * 4u;
 
+    int st = 0;
+    uint32_t phase = 0;
     for (int i = 0; i < n_tiles; ++i) {
-        const int st = i & 1;
-        hfa_mbar_wait(&bar[st], (uint32_t)((i >> 1) & 1));
-        const float *tl = tile0 + st * TILE_FLOATS + first;
-        const float2 *et = edge0 + st * HFA_TILE_T;
-        const int rows = min(HFA_TILE_T, T - i * HFA_TILE_T);
-        int tt = 0;
+        hfa_mbar_wait(&bar[st], phase);
+        const uint32_t tl = tile_sa + (uint32_t)st * (TILE_FLOATS * 4u);
+        const uint32_t et = edge_sa + (uint32_t)st * (TT * 8u);
+        const int rows = min(TT, T - i * TT);
+        const int sh = (i & 1) * TT;                         // bit position of this tile's frame 0
+        uint32_t mbit = 1u << sh;                             // backpointer bit of the current frame
+        // one frame; operands of the NEXT frame (en / edn) are fetched before this frame's dependent
+        // chain -- for the last row of a stage that reads the next stage / the slack row (discarded)
+        auto frame = [&](int tt, const float (&e)[K], const float2 ed, float (&en)[K], float2 &edn) {
+            hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, en);
+            edn = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
+            if (tt == 0 && i == 0) {
+                // t = 0 (:250-254): state 0 is seeded, and state 1 too behind a leading SP
 #pragma unroll
-        for (int k = 0; k < K; ++k) bits[k] = 0;
-        if (i == 0) {
-            // t = 0 (:250-254): state 0 is seeded, and state 1 too when the sequence starts with SP
-            float e[K];
-            hfa_load_row<K>(tl, e);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int s = first + k;
-                if (s == 0 || (s == 1 && lead_sp)) {
-                    dp[k] = e[k];
-                    cu[k] = e[k];
+                for (int k = 0; k < K; ++k) {
+                    const int s = first + k;
+                    if (s == 0 || (s == 1 && lead_sp)) {
+                        dp[k] = e[k];
+                        cu[k] = e[k];
+                    }
                 }
-                if (dp_dump != nullptr && s < S) dp_dump[m.cell_off + s] = dp[k];
-            }
-            tt = 1;
-        }
-#pragma unroll 2
-        for (; tt < rows; ++tt) {
-            float e[K], stay[K], adv[K];
-            hfa_load_row<K>(tl + tt * Sp, e);
-            const float2 ed = et[tt];
+            } else {
+                float stay[K], adv[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float base = __fadd_rn(dp[k], e[k]);
-                stay[k] = __fadd_rn(base, ed.y);
-                adv[k] = hfa_advance(__fadd_rn(base, ed.x), cu[k], ratio);
+                for (int k = 0; k < K; ++k) {
+                    const float base = __fadd_rn(dp[k], e[k]);
+                    stay[k] = __fadd_rn(base, ed.y);
+                    adv[k] = hfa_advance(__fadd_rn(base, ed.x), cu[k], ratio);
+                }
+                float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
+                float up2;
+                if constexpr (K >= 2) up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
+                else up2 = __shfl_up_sync(0xffffffffu, adv[0], 2);
+                if (lane == 0) up1 = HFA_NEG_INF;  // state -1 does not exist; up2 is capped by jump_cap
+                hfa_select<K>(e, stay, adv, up1, up2, sp_and, jump_cap, mbit, mbit << 16, dp, cu, bits);
             }
-            float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
-            float up2;
-            if constexpr (K >= 2) up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
-            else up2 = __shfl_up_sync(0xffffffffu, adv[0], 2);
-            if (lane == 0) up1 = HFA_NEG_INF;      // state -1 does not exist; up2 is masked by skip
-            hfa_select<K>(e, stay, adv, up1, up2, sp_mask, skip_mask, 1u << tt, 0x10000u << tt, dp,
-                          cu, bits);
-            if (dp_dump != nullptr) {
-                const int64_t o = m.cell_off + (int64_t)(i * HFA_TILE_T + tt) * S;
+            mbit <<= 1;
+            if constexpr (DUMP) {
+                const int64_t o = m.cell_off + (int64_t)(i * TT + tt) * S;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
                     if (first + k < S) dp_dump[o + first + k] = dp[k];
             }
+        };
+        float ea[K], eb[K];
+        float2 da, db;
+        hfa_lds_row<K>(tl, ea);
+        da = hfa_lds_f2(et);
+        if (rows == TT) {
+            // full tile: straight-line code, the two operand sets ping-pong without copies
+#pragma unroll
+            for (int tt = 0; tt < TT; tt += 2) {
+                frame(tt, ea, da, eb, db);
+                frame(tt + 1, eb, db, ea, da);
+            }
+        } else {
+            for (int tt = 0; tt < rows; ++tt) {               // last, partial tile
+                frame(tt, ea, da, eb, db);
+#pragma unroll
+                for (int k = 0; k < K; ++k) ea[k] = eb[k];
+                da = db;
+            }
         }
-        hfa_store_bits<K>(g_bp + (int64_t)i * Sp + first, bits, first, Sp);
-        __syncwarp();                               // every lane is done reading stage `st`
-        if (lane == 0 && i + 2 < n_tiles) issue(i + 2);
+        if ((i & 1) || i == n_tiles - 1) {                   // 16 frames done (or the end): flush
+            hfa_store_bits<K>(g_bp + (int64_t)(i >> 1) * Sp + first, bits, first, Sp);
+#pragma unroll
+            for (int k = 0; k < K; ++k) bits[k] = 0;
+        }
+        __syncwarp();                                        // every lane is done reading stage `st`
+        if (lane == 0 && i + NST < n_tiles) issue(i + NST);
+        if (++st == NST) {
+            st = 0;
+            phase ^= 1u;
+        }
     }
 
     // scores of the last two states at T-1 for the end-state rule (:269-272)
@@ -230,6 +312,36 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
     for (int k = 0; k < K; ++k) {
         if (first + k == S - 1) ws.dp_last[2 * u] = dp[k];
         if (first + k == S - 2) ws.dp_last[2 * u + 1] = dp[k];
+    }
+}
+
+// one state class per launch (used when the classes are spread over streams)
+template <int K, bool DUMP>
+__global__ void __launch_bounds__(32)
+hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restrict__ dp_dump)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    hfa_dp_warp_body<K, DUMP>(ws, order[blockIdx.x], dp_dump, smem_raw);
+}
+
+// every state class in ONE launch: each single-warp CTA picks the code path of its utterance.  All
+// CTAs get the shared memory of the largest class present, the block scheduler sees one globally
+// longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.
+template <bool DUMP>
+__global__ void __launch_bounds__(32)
+hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restrict__ dp_dump)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int u = order[blockIdx.x];
+    switch ((ws.utt[u].Sp + 31) >> 5) {
+        case 1: hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 2: hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 3: hfa_dp_warp_body<3, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 4: hfa_dp_warp_body<4, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 5: hfa_dp_warp_body<5, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 6: hfa_dp_warp_body<6, DUMP>(ws, u, dp_dump, smem_raw); break;
+        case 7: hfa_dp_warp_body<7, DUMP>(ws, u, dp_dump, smem_raw); break;
+        default: hfa_dp_warp_body<8, DUMP>(ws, u, dp_dump, smem_raw); break;
     }
 }
 
@@ -280,8 +392,9 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
         hfa_fence_mbar_init();
         for (int i = 0; i < HFA_CTA_STAGES && i < n_tiles; ++i) issue(i);
     }
-    uint32_t sp_mask, skip_mask;
-    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_mask, skip_mask);
+    uint32_t sp_and[K];
+    float jump_cap[K];
+    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
     const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
     __syncthreads();
 
@@ -342,7 +455,7 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
                 }
             }
             const int b = t & 15;
-            hfa_select<K>(e, stay, adv, up1, up2, sp_mask, skip_mask, 1u << b, 0x10000u << b, dp, cu,
+            hfa_select<K>(e, stay, adv, up1, up2, sp_and, jump_cap, 1u << b, 0x10000u << b, dp, cu,
                           bits);
             if (dp_dump != nullptr) {
                 const int64_t o = m.cell_off + (int64_t)t * S;
@@ -374,16 +487,49 @@ template <int K>
 cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    const size_t smem = 2 * HFA_TILE_T * 32 * K * sizeof(float) + 2 * HFA_TILE_T * sizeof(float2) +
-                        2 * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_kernel<K>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hfa_dp_warp_kernel<K><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
+    const size_t smem = hfa_warp_smem_bytes<K>();
+    cudaError_t e;
+    if (dp_dump != nullptr) {
+        e = cudaFuncSetAttribute(hfa_dp_warp_kernel<K, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_dp_warp_kernel<K, true><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
+    } else {
+        e = cudaFuncSetAttribute(hfa_dp_warp_kernel<K, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_dp_warp_kernel<K, false><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
+    }
     return cudaGetLastError();
 }
 
 }  // namespace
+
+// all warp-kernel classes in one launch; max_k = largest states-per-lane class present
+cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
+                                   float *dp_dump)
+{
+    if (n <= 0) return cudaSuccess;
+    static const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(), hfa_warp_smem_bytes<2>(),
+                                    hfa_warp_smem_bytes<3>(), hfa_warp_smem_bytes<4>(),
+                                    hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),
+                                    hfa_warp_smem_bytes<7>(), hfa_warp_smem_bytes<8>()};
+    if (max_k < 1 || max_k > 8) return cudaErrorInvalidValue;
+    const size_t smem = bytes[max_k];
+    cudaError_t e;
+    if (dp_dump != nullptr) {
+        e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes[8]);
+        if (e != cudaSuccess) return e;
+        hfa_dp_warp_any_kernel<true><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
+    } else {
+        e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes[8]);
+        if (e != cudaSuccess) return e;
+        hfa_dp_warp_any_kernel<false><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
+    }
+    return cudaGetLastError();
+}
 
 // order: device pointer to the utterance indices of this class; n: how many
 cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,

@@ -58,15 +58,27 @@ __device__ __forceinline__ void edge_logs(float p, float p_prev, float2 &out)
     out.y = (float)log(__dadd_rn(__dsub_rn(1.0, ep), 1e-6));          // :242  (1 - ep) + 1e-6
 }
 
-template <typename TIn>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// VPL = vocabulary entries per lane (V <= 32 * VPL) for the register-staged path, 0 = any V.
+// Shared memory: ids [sp_cap] (pads -> V), keep-mask words, row buffers [warps][rows][V + 1] whose
+// extra slot V holds -inf: a pad column gathers that slot and comes out as -inf without a select.
+template <typename TIn, int VPL>
 __global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)
 hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
 {
+    constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;                      // rows per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *ids_sm = reinterpret_cast<int32_t *>(smem_raw);                 // [sp_cap]
     uint32_t *mask_sm = reinterpret_cast<uint32_t *>(ids_sm + sp_cap);       // [ceil(V/32)] keep bits
     const int mask_words = (V + 31) >> 5;
-    float *rows_sm = reinterpret_cast<float *>(mask_sm + ((mask_words + 3) & ~3));  // [warps][V]
+    float *rows_sm = reinterpret_cast<float *>(mask_sm + ((mask_words + 3) & ~3));
+    const int VS = V + 1;                                                    // row buffer stride
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u = find_utt(ws.row_blocks, n_utt, blockIdx.x);
@@ -74,100 +86,141 @@ hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     const HfaInput in = ws.inputs[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+    const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
+    float *g_out = ws.emis + m.emis_off;
 
+    // (1) every warp puts the loads of ALL its rows in flight before anything else
+    float x[RPW][VPL > 0 ? VPL : 1];
+    if constexpr (VPL > 0) {
+        const TIn *src0 = frame + (int64_t)(t_base + warp) * in.frame_st + (int64_t)lane * in.frame_sv;
+        const int64_t row_step = (int64_t)HFA_EMIS_WARPS * in.frame_st;
+        const int64_t col_step = 32 * in.frame_sv;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const bool row_ok = t_base + warp + HFA_EMIS_WARPS * r < T;
+#pragma unroll
+            for (int q = 0; q < VPL; ++q)
+                x[r][q] = (row_ok && lane + 32 * q < V)
+                              ? hfa_to_float<TIn>(src0[r * row_step + q * col_step]) : HFA_NEG_INF;
+        }
+    }
+
+    // (2) phoneme ids and the keep-mask of this utterance -> shared memory
     for (int w = tid; w < mask_words; w += blockDim.x) mask_sm[w] = (w == 0) ? 1u : 0u;  // id 0 (:39)
     __syncthreads();
     const int32_t *ids = ws.ids + m.seg_off;
     for (int s = tid; s < Sp; s += blockDim.x) {
-        const int id = (s < S) ? ids[s] : 0;
+        const int id = (s < S) ? ids[s] : V;
         ids_sm[s] = id;
-        atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
     }
     __syncthreads();
 
-    const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
-    float *rowbuf = rows_sm + warp * V;
-    float *g_out = ws.emis + m.emis_off;
+    if constexpr (VPL > 0) {
+        float *rowbuf = rows_sm + (size_t)warp * RPW * VS;
+        const uint32_t rowbuf_sa = hfa_smem_u32(rowbuf);
+        if (lane < RPW) rowbuf[lane * VS + V] = HFA_NEG_INF;                 // the pad sentinel
+        // per-lane constants: the 1e9 penalty of its vocabulary entries (:53) and the byte offsets
+        // of the (up to 8) row-buffer slots it gathers
+        float pen[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+            const int v = lane + 32 * q;
+            pen[q] = (v < V && !((mask_sm[v >> 5] >> (v & 31)) & 1u)) ? 1e9f : 0.0f;
+        }
+        uint32_t goff[2][4];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int s4 = lane * 4 + 128 * it;
+            int4 id4 = make_int4(V, V, V, V);
+            if (s4 < Sp) id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+            goff[it][0] = (uint32_t)id4.x * 4u; goff[it][1] = (uint32_t)id4.y * 4u;
+            goff[it][2] = (uint32_t)id4.z * 4u; goff[it][3] = (uint32_t)id4.w * 4u;
+        }
 
-    if (V <= 32 * HFA_EMIS_MAX_VPL) {
-        // two rows per iteration, values staged in registers
-        for (int j = 0; j < HFA_EMIS_ROWS / HFA_EMIS_WARPS; j += 2) {
-            float x[2][HFA_EMIS_MAX_VPL];
-            int tr[2];
+        // (3) masked max / log-sum-exp of the 8 rows (independent chains), rows parked in smem
+        float mx[RPW], lse[RPW];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                tr[r] = t_base + warp + HFA_EMIS_WARPS * (j + r);
-                const TIn *src = frame + (int64_t)tr[r] * in.frame_st;
+        for (int r = 0; r < RPW; ++r) {
+            float mr = HFA_NEG_INF;
 #pragma unroll
-                for (int q = 0; q < HFA_EMIS_MAX_VPL; ++q) {
-                    const int v = lane + 32 * q;
-                    x[r][q] = HFA_NEG_INF;
-                    if (tr[r] < T && v < V) {
-                        float xv = hfa_to_float<TIn>(src[(int64_t)v * in.frame_sv]);
-                        if (!((mask_sm[v >> 5] >> (v & 31)) & 1u)) xv = __fsub_rn(xv, 1e9f);  // :53
-                        x[r][q] = xv;
-                    }
+            for (int q = 0; q < VPL; ++q) {
+                x[r][q] = __fsub_rn(x[r][q], pen[q]);                        // :53 (x - 0 is exact)
+                mr = fmaxf(mr, x[r][q]);
+            }
+            mx[r] = warp_max(mr);
+        }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) {
+                if (lane + 32 * q < V) {
+                    sum = __fadd_rn(sum, expf(__fsub_rn(x[r][q], mx[r])));
+                    rowbuf[r * VS + lane + 32 * q] = x[r][q];
                 }
             }
+            lse[r] = logf(warp_sum(sum));
+        }
+        __syncwarp();
+
+        // (4) gather by phoneme id and store: out[t][s] = (x[id[s]] - max) - lse
+        float *dst = g_out + (int64_t)(t_base + warp) * Sp + lane * 4;
+        const int64_t dst_step = (int64_t)HFA_EMIS_WARPS * Sp;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (tr[r] >= T) continue;                    // warp-uniform
-                float mx = x[r][0];
+        for (int r = 0; r < RPW; ++r) {
+            if (t_base + warp + HFA_EMIS_WARPS * r >= T) break;              // warp-uniform
+            const uint32_t rb = rowbuf_sa + (uint32_t)(r * VS) * 4u;
 #pragma unroll
-                for (int q = 1; q < HFA_EMIS_MAX_VPL; ++q) mx = fmaxf(mx, x[r][q]);
-                mx = warp_max(mx);
-                float sum = 0.0f;
-#pragma unroll
-                for (int q = 0; q < HFA_EMIS_MAX_VPL; ++q) {
-                    const int v = lane + 32 * q;
-                    if (v < V) {
-                        sum = __fadd_rn(sum, expf(__fsub_rn(x[r][q], mx)));
-                        rowbuf[v] = x[r][q];
-                    }
-                }
-                sum = warp_sum(sum);
-                const float lse = logf(sum);
-                __syncwarp();
-                float *dst = g_out + (int64_t)tr[r] * Sp;
-                for (int s4 = lane * 4; s4 < Sp; s4 += 128) {
-                    const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+            for (int it = 0; it < 2; ++it) {
+                if (lane * 4 + 128 * it < Sp) {
                     float4 o;
-                    o.x = (s4 + 0 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.x], mx), lse) : HFA_NEG_INF;
-                    o.y = (s4 + 1 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.y], mx), lse) : HFA_NEG_INF;
-                    o.z = (s4 + 2 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.z], mx), lse) : HFA_NEG_INF;
-                    o.w = (s4 + 3 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.w], mx), lse) : HFA_NEG_INF;
-                    *reinterpret_cast<float4 *>(dst + s4) = o;
+                    o.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][0]), mx[r]), lse[r]);
+                    o.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][1]), mx[r]), lse[r]);
+                    o.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][2]), mx[r]), lse[r]);
+                    o.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][3]), mx[r]), lse[r]);
+                    *reinterpret_cast<float4 *>(dst + r * dst_step + 128 * it) = o;
                 }
-                __syncwarp();
+            }
+            for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {              // S > 256 only
+                const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+                float4 o;
+                o.x = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.x], mx[r]), lse[r]);
+                o.y = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.y], mx[r]), lse[r]);
+                o.z = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.z], mx[r]), lse[r]);
+                o.w = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.w], mx[r]), lse[r]);
+                *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
             }
         }
     } else {
         // wide vocabularies: one row at a time through the shared-memory row buffer
-        for (int j = 0; j < HFA_EMIS_ROWS / HFA_EMIS_WARPS; ++j) {
+        float *rowbuf = rows_sm + (size_t)warp * VS;
+        if (lane == 0) rowbuf[V] = HFA_NEG_INF;
+        __syncwarp();
+        for (int j = 0; j < RPW; ++j) {
             const int t = t_base + warp + HFA_EMIS_WARPS * j;
             if (t >= T) continue;
             const TIn *src = frame + (int64_t)t * in.frame_st;
-            float mx = HFA_NEG_INF;
+            float mr = HFA_NEG_INF;
             for (int v = lane; v < V; v += 32) {
                 float xv = hfa_to_float<TIn>(src[(int64_t)v * in.frame_sv]);
                 if (!((mask_sm[v >> 5] >> (v & 31)) & 1u)) xv = __fsub_rn(xv, 1e9f);
                 rowbuf[v] = xv;
-                mx = fmaxf(mx, xv);
+                mr = fmaxf(mr, xv);
             }
-            mx = warp_max(mx);
+            mr = warp_max(mr);
             float sum = 0.0f;
-            for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, expf(__fsub_rn(rowbuf[v], mx)));
-            sum = warp_sum(sum);
-            const float lse = logf(sum);
+            for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, expf(__fsub_rn(rowbuf[v], mr)));
+            const float l = logf(warp_sum(sum));
             __syncwarp();
             float *dst = g_out + (int64_t)t * Sp;
             for (int s4 = lane * 4; s4 < Sp; s4 += 128) {
                 const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
                 float4 o;
-                o.x = (s4 + 0 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.x], mx), lse) : HFA_NEG_INF;
-                o.y = (s4 + 1 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.y], mx), lse) : HFA_NEG_INF;
-                o.z = (s4 + 2 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.z], mx), lse) : HFA_NEG_INF;
-                o.w = (s4 + 3 < S) ? __fsub_rn(__fsub_rn(rowbuf[id4.w], mx), lse) : HFA_NEG_INF;
+                o.x = __fsub_rn(__fsub_rn(rowbuf[id4.x], mr), l);
+                o.y = __fsub_rn(__fsub_rn(rowbuf[id4.y], mr), l);
+                o.z = __fsub_rn(__fsub_rn(rowbuf[id4.z], mr), l);
+                o.w = __fsub_rn(__fsub_rn(rowbuf[id4.w], mr), l);
                 *reinterpret_cast<float4 *>(dst + s4) = o;
             }
             __syncwarp();
@@ -217,26 +270,39 @@ hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
 
 }  // namespace
 
+template <typename TIn>
+static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_sp)
+{
+    const int V = c.vocab;
+    const int vpl = (V + 31) / 32;
+    const int mask_words = (V + 31) >> 5;
+    const size_t rows = (vpl <= HFA_EMIS_MAX_VPL) ? (size_t)HFA_EMIS_ROWS : (size_t)HFA_EMIS_WARPS;
+    const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 + rows * (V + 1) * 4;
+    cudaError_t e;
+#define HFA_EMIS_LAUNCH(VPL)                                                                       \
+    e = cudaFuncSetAttribute(hfa_emission_kernel<TIn, VPL>,                                        \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return e;                                                                \
+    hfa_emission_kernel<TIn, VPL><<<blocks, HFA_EMIS_WARPS * 32, smem, c.stream>>>(c.ws, c.n_utt,  \
+                                                                                  V, max_sp)
+    switch (vpl <= HFA_EMIS_MAX_VPL ? vpl : 0) {
+        case 1: HFA_EMIS_LAUNCH(1); break;
+        case 2: HFA_EMIS_LAUNCH(2); break;
+        case 3: HFA_EMIS_LAUNCH(3); break;
+        case 4: HFA_EMIS_LAUNCH(4); break;
+        default: HFA_EMIS_LAUNCH(0); break;
+    }
+#undef HFA_EMIS_LAUNCH
+    return cudaGetLastError();
+}
+
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype)
 {
     if (total_row_blocks <= 0) return cudaSuccess;
-    const int V = c.vocab;
-    const int mask_words = (V + 31) >> 5;
-    const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 +
-                        (size_t)HFA_EMIS_WARPS * V * 4;
-    cudaError_t e;
-#define HFA_EMIS_LAUNCH(TIn)                                                                       \
-    e = cudaFuncSetAttribute(hfa_emission_kernel<TIn>,                                             \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-    if (e != cudaSuccess) return e;                                                                \
-    hfa_emission_kernel<TIn><<<total_row_blocks, HFA_EMIS_WARPS * 32, smem, c.stream>>>(           \
-        c.ws, c.n_utt, V, max_sp)
-    if (dtype == 0) { HFA_EMIS_LAUNCH(float); }
-    else if (dtype == 1) { HFA_EMIS_LAUNCH(__half); }
-    else if (dtype == 2) { HFA_EMIS_LAUNCH(__nv_bfloat16); }
-    else return cudaErrorInvalidValue;
-#undef HFA_EMIS_LAUNCH
-    return cudaGetLastError();
+    if (dtype == 0) return launch_emission_t<float>(c, total_row_blocks, max_sp);
+    if (dtype == 1) return launch_emission_t<__half>(c, total_row_blocks, max_sp);
+    if (dtype == 2) return launch_emission_t<__nv_bfloat16>(c, total_row_blocks, max_sp);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const float *prob_log,

@@ -1,0 +1,173 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/hfa_align.h, the collation
+("plan") logic, the batched SP-filter / word-merge, sharding, and the no-fallback guarantees."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hubertfa_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hfa_align.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hfa_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in hfa_align.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "python binding and header disagree"
+    assert _lib.load().hfa_abi_version() == _lib.ABI_VERSION
+
+
+def test_plan_layout_and_statuses():
+    from hubertfa_b200 import ops
+    T = [500, 0, 30, 17, 40]
+    S = [40, 3, 300, 0, 5]
+    ids = np.zeros(sum(S), np.int32)
+    ids[-1] = 99                      # out of range for V = 63 -> BAD_ID for the last utterance
+    p = ops.AlignPlan(T, S, ids, 63, 0.02)
+    assert list(p.seg_off) == [0, 40, 43, 343, 343, 348]
+    assert list(p.frame_off) == [0, 500, 500, 530, 530, 530]
+    assert p.total_cells == 500 * 40 + 30 * 300
+    assert p.total_frames == 530
+    L = p.layout
+    offs = [L.status, L.n_seg, L.end_state, L.final_score, L.total_conf, L.ph_idx_seq, L.ph_time_int,
+            L.intervals]
+    assert offs == sorted(offs) and all(o % 16 == 0 for o in offs) and L.total_bytes >= offs[-1] + 16 * 348
+    alg = p.algorithmic_bytes()
+    assert alg["dp"] == p.total_cells * 4 + p.total_frames * 8 + 4 * (32 * 40 + 2 * 300)
+    assert alg["emission"] == p.total_frames * (63 * 4 + 4) + p.total_cells * 4 + p.total_frames * 12
+    p.close()
+    with pytest.raises(Exception):
+        ops.AlignPlan([1, 2], [1], np.zeros(1, np.int32), 63, 0.02)
+    empty = ops.AlignPlan([], [], np.zeros(0, np.int32), 63, 0.02)
+    assert empty.total_cells == 0 and empty.workspace_bytes >= 0
+
+
+def test_compute_entry_points_fail_loudly_without_cuda():
+    import torch
+    from hubertfa_b200 import ops
+    from hubertfa_b200._lib import HfaError
+    from hubertfa_b200.alignment_decoder import AlignmentDecoder
+    if torch.cuda.is_available():
+        pytest.skip("this checks the CPU-only behaviour")
+    dec = AlignmentDecoder({"vocab": {"SP": 0, "a": 1}, "vocab_size": 2}, {"hop_length": 512, "sample_rate": 44100})
+    with pytest.raises((HfaError, RuntimeError)):
+        dec.decode(torch.zeros(1, 5, 2), torch.zeros(1, 5), torch.zeros(1, 5, 2), None, ["SP", "a", "SP"])
+    p = ops.AlignPlan([5], [3], np.array([0, 1, 0], np.int32), 2, 0.01)
+    with pytest.raises((HfaError, RuntimeError, NotImplementedError)):
+        ops.emission(torch.zeros(p.workspace_bytes, dtype=torch.uint8), p.handle, 0)
+
+
+def test_decoder_raises_like_the_reference():
+    from hubertfa_b200.alignment_decoder import AlignmentDecoder
+    import torch
+    dec = AlignmentDecoder({"vocab": {"SP": 0, "a": 1}, "vocab_size": 2}, {"hop_length": 512, "sample_rate": 44100})
+    with pytest.raises(KeyError):                       # alignment_decoder.py:35
+        dec.decode(torch.zeros(1, 5, 2), torch.zeros(1, 5), None, None, ["SP", "zz"])
+
+
+def test_product_never_touches_the_oracle():
+    """hubertfa_b200/ must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "hubertfa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "synth.py", f"{f} mentions the oracle"
+    code = ("import sys; sys.path.insert(0, %r); import hubertfa_b200, hubertfa_b200.ops, "
+            "hubertfa_b200.alignment_decoder, hubertfa_b200.sharding; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_batch_filter_and_merge_matches_the_reference_loop():
+    """BatchAlignment's vectorised SP filter / word merge == the oracle's per-utterance loop
+    (alignment_decoder.py:115-138) on fabricated raw segments (no GPU needed)."""
+    from hubertfa_b200 import ops, synth
+    from hubertfa_b200.alignment_decoder import BatchAlignment
+    from oracle import hfa_oracle_np as onp
+    rng = np.random.default_rng(3)
+    n, V = 7, 39
+    T = rng.integers(30, 90, n).astype(np.int32)
+    S = rng.integers(1, 25, n).astype(np.int32)
+    seqs = [synth.make_ph_seq(rng, int(s), V, ["dictionary", "alternate", "nosp"][i % 3]) for i, s in enumerate(S)]
+    ids = np.concatenate([[0 if p == "SP" else int(p[1:]) for p in q[0]] for q in seqs]).astype(np.int32)
+    plan = ops.AlignPlan(T, S, ids, V, 0.02)
+    blob = np.zeros(plan.result_bytes, np.uint8)
+    v = plan.views(blob)
+    raw = []
+    for b in range(n):
+        k = int(rng.integers(1, S[b] + 1))
+        idx = np.sort(rng.choice(S[b], size=k, replace=False))
+        tim = np.sort(rng.choice(T[b], size=k, replace=False))
+        tim[0] = 0
+        times = np.concatenate([tim * 0.02 + rng.uniform(-0.01, 0.01, k), [T[b] * 0.02]])
+        iv = np.stack([times[:-1], times[1:]], axis=1)
+        o = int(plan.seg_off[b])
+        v["n_seg"][b] = k
+        v["ph_idx_seq"][o:o + k] = idx
+        v["ph_time_int"][o:o + k] = tim
+        v["intervals"][o:o + k] = iv
+        v["total_conf"][b] = 0.5
+        raw.append((idx, iv))
+    is_sp = np.concatenate([np.array([p == "SP" for p in q[0]]) for q in seqs])
+    widx = np.concatenate([np.asarray(q[2], dtype=np.int64) for q in seqs])
+    res = BatchAlignment(plan, v, [q[0] for q in seqs], [q[1] for q in seqs], [q[2] for q in seqs], is_sp, widx)
+    for b in range(n):
+        want = onp.filter_and_merge(seqs[b][0], raw[b][0], raw[b][1], seqs[b][1], seqs[b][2])
+        got = res[b]
+        assert list(got[0]) == list(want[0]) and list(got[2]) == list(want[2])
+        assert np.array_equal(got[1].reshape(want[1].shape), want[1])
+        assert np.array_equal(got[3].reshape(want[3].shape), want[3])
+
+
+def test_sharding_balances_cost_and_keeps_every_utterance():
+    from hubertfa_b200 import sharding, synth
+    T, S = synth.sample_shapes(1000, seed=1)
+    for world in (1, 2, 4, 8):
+        shards = sharding.shard_by_cost(T, S, world)
+        allidx = np.sort(np.concatenate(shards))
+        assert np.array_equal(allidx, np.arange(1000))
+        cost = np.array([(T[s].astype(np.int64) * S[s]).sum() for s in shards])
+        assert cost.max() <= 1.02 * cost.mean()
+    chunks = sharding.chunk_by_bytes(T, S, max_cells=2_000_000)
+    assert np.array_equal(np.concatenate(chunks), np.arange(1000))
+    assert all((T[c].astype(np.int64) * S[c]).sum() <= 2_000_000 or len(c) == 1 for c in chunks)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from hubertfa_b200 import sharding, synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    T, S = synth.sample_shapes(40, seed=9)
+    mine = sharding.shard_by_cost(T, S, world)[rank]
+    payload = {"n_seg": [int(S[i]) for i in mine], "tag": [f"utt{int(i)}@{rank}" for i in mine]}
+    out = sharding.gather_on_host(mine, payload)
+    if rank == 0:
+        q.put((out["n_seg"], out["tag"]))
+    dist.destroy_process_group()
+
+
+def test_gather_on_host_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    from hubertfa_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n_seg, tag = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    T, S = synth.sample_shapes(40, seed=9)
+    assert n_seg == [int(s) for s in S]
+    assert all(t.startswith(f"utt{i}@") for i, t in enumerate(tag))
