@@ -20,6 +20,8 @@
 //
 // HBM traffic per DP cell: 4 B emission read + 2 bits backpointer write (+ 8 B per frame of edge
 // logs) = the 4.25 B/cell "algorithmic bytes" of DESIGN.md.
+#include <cstdlib>
+
 #include "hfa_common.cuh"
 
 namespace {
@@ -184,7 +186,7 @@ __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
     float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + ROW_MAX);
     uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
 
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const HfaUtt m = ws.utt[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int first = lane * K;
@@ -280,8 +282,10 @@ __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
         hfa_lds_row<K>(tl, ea);
         da = hfa_lds_f2(et);
         if (rows == TT) {
-            // full tile: straight-line code, the two operand sets ping-pong without copies
-#pragma unroll
+            // full tile: the two operand sets ping-pong without copies.  NOT unrolled further: the
+            // merged kernel keeps up to 8 code paths hot per SM and must fit the instruction cache
+            // (ncu: stall_no_instruction dominated when this loop was fully unrolled).
+#pragma unroll 1
             for (int tt = 0; tt < TT; tt += 2) {
                 frame(tt, ea, da, eb, db);
                 frame(tt + 1, eb, db, ea, da);
@@ -324,15 +328,20 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
     hfa_dp_warp_body<K, DUMP>(ws, order[blockIdx.x], dp_dump, smem_raw);
 }
 
-// every state class in ONE launch: each single-warp CTA picks the code path of its utterance.  All
-// CTAs get the shared memory of the largest class present, the block scheduler sees one globally
-// longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.
-template <bool DUMP>
-__global__ void __launch_bounds__(32)
-hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restrict__ dp_dump)
+// every state class in ONE launch: each warp picks the code path of its utterance.  All warps get
+// the shared memory of the largest class present, the block scheduler sees one globally
+// longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.  WPC warps per
+// CTA (one utterance each, no interaction between them); HFA_DP_WPC=4 packs four per CTA.
+template <bool DUMP, int WPC>
+__global__ void __launch_bounds__(32 * WPC)
+hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int smem_per_warp,
+                       float *__restrict__ dp_dump)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int u = order[blockIdx.x];
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    if (item >= n) return;
+    unsigned char *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * smem_per_warp;
+    const int u = order[item];
     switch ((ws.utt[u].Sp + 31) >> 5) {
         case 1: hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw); break;
         case 2: hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw); break;
@@ -505,6 +514,19 @@ cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, floa
 
 }  // namespace
 
+template <bool DUMP, int WPC>
+static cudaError_t launch_any(const HfaLaunchCtx &c, size_t per_warp, const int32_t *order, int n,
+                              float *dp_dump)
+{
+    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, WPC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(WPC * ((hfa_warp_smem_bytes<8>() + 127) & ~(size_t)127)));
+    if (e != cudaSuccess) return e;
+    hfa_dp_warp_any_kernel<DUMP, WPC><<<(n + WPC - 1) / WPC, 32 * WPC, WPC * per_warp, c.stream>>>(
+        c.ws, order, n, (int)per_warp, dp_dump);
+    return cudaGetLastError();
+}
+
 // all warp-kernel classes in one launch; max_k = largest states-per-lane class present
 cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
                                    float *dp_dump)
@@ -515,20 +537,16 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
                                     hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),
                                     hfa_warp_smem_bytes<7>(), hfa_warp_smem_bytes<8>()};
     if (max_k < 1 || max_k > 8) return cudaErrorInvalidValue;
-    const size_t smem = bytes[max_k];
-    cudaError_t e;
-    if (dp_dump != nullptr) {
-        e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes[8]);
-        if (e != cudaSuccess) return e;
-        hfa_dp_warp_any_kernel<true><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
-    } else {
-        e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes[8]);
-        if (e != cudaSuccess) return e;
-        hfa_dp_warp_any_kernel<false><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
-    }
-    return cudaGetLastError();
+    const size_t per_warp = (bytes[max_k] + 127) & ~(size_t)127;
+    static const int wpc = [] {
+        const char *e = getenv("HFA_DP_WPC");
+        return (e && e[0] == '4') ? 4 : 1;   // measured on B200: 1 warp per CTA is the faster one
+    }();
+    if (dp_dump != nullptr)
+        return wpc == 1 ? launch_any<true, 1>(c, per_warp, order, n, dp_dump)
+                        : launch_any<true, 4>(c, per_warp, order, n, dp_dump);
+    return wpc == 1 ? launch_any<false, 1>(c, per_warp, order, n, dp_dump)
+                    : launch_any<false, 4>(c, per_warp, order, n, dp_dump);
 }
 
 // order: device pointer to the utterance indices of this class; n: how many

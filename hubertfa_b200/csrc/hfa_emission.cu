@@ -89,20 +89,23 @@ hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
     float *g_out = ws.emis + m.emis_off;
 
-    // (1) every warp puts the loads of ALL its rows in flight before anything else
+    // (1) every warp puts the loads of ALL its rows in flight before anything else.  Branch-free:
+    //     out-of-range lanes / rows read a clamped (valid) address and are replaced by -inf.
     float x[RPW][VPL > 0 ? VPL : 1];
     if constexpr (VPL > 0) {
-        const TIn *src0 = frame + (int64_t)(t_base + warp) * in.frame_st + (int64_t)lane * in.frame_sv;
         const int64_t row_step = (int64_t)HFA_EMIS_WARPS * in.frame_st;
-        const int64_t col_step = 32 * in.frame_sv;
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const bool row_ok = t_base + warp + HFA_EMIS_WARPS * r < T;
+        for (int q = 0; q < VPL; ++q) {
+            const int v = lane + 32 * q;
+            const TIn *col = frame + (int64_t)min(v, V - 1) * in.frame_sv;
 #pragma unroll
-            for (int q = 0; q < VPL; ++q)
-                x[r][q] = (row_ok && lane + 32 * q < V)
-                              ? hfa_to_float<TIn>(src0[r * row_step + q * col_step]) : HFA_NEG_INF;
+            for (int r = 0; r < RPW; ++r) {
+                const int t = min(t_base + warp + HFA_EMIS_WARPS * r, T - 1);
+                const float xv = hfa_to_float<TIn>(col[(int64_t)t * in.frame_st]);
+                x[r][q] = (v < V) ? xv : HFA_NEG_INF;
+            }
         }
+        (void)row_step;
     }
 
     // (2) phoneme ids and the keep-mask of this utterance -> shared memory
@@ -117,23 +120,24 @@ hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     __syncthreads();
 
     if constexpr (VPL > 0) {
-        float *rowbuf = rows_sm + (size_t)warp * RPW * VS;
+        // row buffers: stride 32*VPL+1 so every lane stores unconditionally; slots V.. hold the -inf
+        // of the out-of-range lanes, which is exactly the pad sentinel the gather needs at slot V
+        constexpr int RS = 32 * VPL + 1;
+        float *rowbuf = rows_sm + (size_t)warp * RPW * RS;
         const uint32_t rowbuf_sa = hfa_smem_u32(rowbuf);
-        if (lane < RPW) rowbuf[lane * VS + V] = HFA_NEG_INF;                 // the pad sentinel
         // per-lane constants: the 1e9 penalty of its vocabulary entries (:53) and the byte offsets
         // of the (up to 8) row-buffer slots it gathers
         float pen[VPL];
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
-            const int v = lane + 32 * q;
-            pen[q] = (v < V && !((mask_sm[v >> 5] >> (v & 31)) & 1u)) ? 1e9f : 0.0f;
+            const int v = min(lane + 32 * q, V - 1);
+            pen[q] = ((mask_sm[v >> 5] >> (v & 31)) & 1u) ? 0.0f : 1e9f;
         }
         uint32_t goff[2][4];
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int s4 = lane * 4 + 128 * it;
-            int4 id4 = make_int4(V, V, V, V);
-            if (s4 < Sp) id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+            const int s4 = min(lane * 4 + 128 * it, Sp - 4);
+            const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
             goff[it][0] = (uint32_t)id4.x * 4u; goff[it][1] = (uint32_t)id4.y * 4u;
             goff[it][2] = (uint32_t)id4.z * 4u; goff[it][3] = (uint32_t)id4.w * 4u;
         }
@@ -155,41 +159,47 @@ hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
             float sum = 0.0f;
 #pragma unroll
             for (int q = 0; q < VPL; ++q) {
-                if (lane + 32 * q < V) {
-                    sum = __fadd_rn(sum, expf(__fsub_rn(x[r][q], mx[r])));
-                    rowbuf[r * VS + lane + 32 * q] = x[r][q];
-                }
+                sum = __fadd_rn(sum, expf(__fsub_rn(x[r][q], mx[r])));       // exp(-inf) = 0 for v >= V
+                rowbuf[r * RS + lane + 32 * q] = x[r][q];
             }
             lse[r] = logf(warp_sum(sum));
         }
         __syncwarp();
 
         // (4) gather by phoneme id and store: out[t][s] = (x[id[s]] - max) - lse
+        const int rows_here = min(RPW, (T - t_base - warp + HFA_EMIS_WARPS - 1) / HFA_EMIS_WARPS);
         float *dst = g_out + (int64_t)(t_base + warp) * Sp + lane * 4;
-        const int64_t dst_step = (int64_t)HFA_EMIS_WARPS * Sp;
+        const int dst_step = HFA_EMIS_WARPS * Sp;
+        const bool st0 = lane * 4 < Sp, st1 = lane * 4 + 128 < Sp;
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-            if (t_base + warp + HFA_EMIS_WARPS * r >= T) break;              // warp-uniform
-            const uint32_t rb = rowbuf_sa + (uint32_t)(r * VS) * 4u;
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                if (lane * 4 + 128 * it < Sp) {
-                    float4 o;
-                    o.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][0]), mx[r]), lse[r]);
-                    o.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][1]), mx[r]), lse[r]);
-                    o.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][2]), mx[r]), lse[r]);
-                    o.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[it][3]), mx[r]), lse[r]);
-                    *reinterpret_cast<float4 *>(dst + r * dst_step + 128 * it) = o;
-                }
+            if (r >= rows_here) break;                                       // warp-uniform
+            const uint32_t rb = rowbuf_sa + (uint32_t)(r * RS) * 4u;
+            float4 o0, o1;
+            o0.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][0]), mx[r]), lse[r]);
+            o0.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][1]), mx[r]), lse[r]);
+            o0.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][2]), mx[r]), lse[r]);
+            o0.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][3]), mx[r]), lse[r]);
+            if (st0) *reinterpret_cast<float4 *>(dst + r * dst_step) = o0;
+            if (Sp > 128) {                                                  // warp-uniform
+                o1.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][0]), mx[r]), lse[r]);
+                o1.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][1]), mx[r]), lse[r]);
+                o1.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][2]), mx[r]), lse[r]);
+                o1.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][3]), mx[r]), lse[r]);
+                if (st1) *reinterpret_cast<float4 *>(dst + r * dst_step + 128) = o1;
             }
-            for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {              // S > 256 only
-                const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
-                float4 o;
-                o.x = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.x], mx[r]), lse[r]);
-                o.y = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.y], mx[r]), lse[r]);
-                o.z = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.z], mx[r]), lse[r]);
-                o.w = __fsub_rn(__fsub_rn(rowbuf[r * VS + id4.w], mx[r]), lse[r]);
-                *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
+        }
+        if (Sp > 256) {                                                      // long phoneme sequences
+            for (int r = 0; r < rows_here; ++r) {
+                for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {
+                    const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+                    float4 o;
+                    o.x = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.x], mx[r]), lse[r]);
+                    o.y = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.y], mx[r]), lse[r]);
+                    o.z = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.z], mx[r]), lse[r]);
+                    o.w = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.w], mx[r]), lse[r]);
+                    *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
+                }
             }
         }
     } else {
@@ -277,7 +287,8 @@ static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_
     const int vpl = (V + 31) / 32;
     const int mask_words = (V + 31) >> 5;
     const size_t rows = (vpl <= HFA_EMIS_MAX_VPL) ? (size_t)HFA_EMIS_ROWS : (size_t)HFA_EMIS_WARPS;
-    const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 + rows * (V + 1) * 4;
+    const size_t stride = (vpl <= HFA_EMIS_MAX_VPL) ? (size_t)(32 * vpl + 1) : (size_t)(V + 1);
+    const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 + rows * stride * 4;
     cudaError_t e;
 #define HFA_EMIS_LAUNCH(VPL)                                                                       \
     e = cudaFuncSetAttribute(hfa_emission_kernel<TIn, VPL>,                                        \
