@@ -95,10 +95,11 @@ struct hfa_plan {
     int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
+    std::vector<int32_t> block_utt;            // [row_blocks[n]]
     int64_t total_frames = 0, total_states = 0, total_cells = 0, padded_cells = 0;
     int64_t total_words = 0, total_edge = 0;
     // byte offsets
-    int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_inputs = 0, head_bytes = 0;
+    int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
             o_last = 0, ws_bytes = 0;
     std::vector<unsigned char> head;           // host image of the head (without inputs)
@@ -115,6 +116,7 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.ids = reinterpret_cast<const int32_t *>(b + p->o_ids);
     w.order = reinterpret_cast<const int32_t *>(b + p->o_order);
     w.row_blocks = reinterpret_cast<const int32_t *>(b + p->o_rowblk);
+    w.block_utt = reinterpret_cast<const int32_t *>(b + p->o_blkutt);
     w.inputs = reinterpret_cast<HfaInput *>(b + p->o_inputs);
     w.emis = reinterpret_cast<float *>(b + p->o_emis);
     w.edge2 = reinterpret_cast<float2 *>(b + p->o_edge2);
@@ -272,6 +274,10 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_ids = region(p->total_states * 4);
         p->o_order = region((int64_t)p->order.size() * 4);
         p->o_rowblk = region((int64_t)(n_utt + 1) * 4);
+        p->block_utt.reserve((size_t)p->row_blocks[n_utt]);
+        for (int32_t b = 0; b < n_utt; ++b)
+            p->block_utt.insert(p->block_utt.end(), (size_t)(p->row_blocks[b + 1] - p->row_blocks[b]), b);
+        p->o_blkutt = region((int64_t)p->block_utt.size() * 4);
         p->head_bytes = o;
         p->o_inputs = region((int64_t)n_utt * sizeof(HfaInput));
         p->o_emis = region(emis * 4);
@@ -292,6 +298,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             std::memcpy(p->head.data() + p->o_order, p->order.data(), p->order.size() * 4);
         }
         std::memcpy(p->head.data() + p->o_rowblk, p->row_blocks.data(), (size_t)(n_utt + 1) * 4);
+        if (!p->block_utt.empty())
+            std::memcpy(p->head.data() + p->o_blkutt, p->block_utt.data(), p->block_utt.size() * 4);
 
         // result blob layout
         int64_t r = 0;

@@ -70,17 +70,34 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     const int s_end = s;
 
     // ---- phase 1: backward walk ----
+    // Lane j holds word(row, s_hi - j) of the row being walked.  Rows are fetched LEAD rows ahead
+    // as 64-state bands below the state the path has at fetch time: the path drops ~T/S... a few
+    // states per 16-frame row, so LEAD rows later the wanted 32 states are almost always inside the
+    // band (otherwise: one exposed reload).  This keeps the load latency off the serial walk.
+    constexpr int LEAD = 4;
     const int n_rows = (T + 15) >> 4;
     int n_seg = 0;
     int s_hi = s;
-    uint32_t W = (s_hi - lane >= 0) ? bp[(int64_t)(n_rows - 1) * Sp + (s_hi - lane)] : 0u;
-    for (int w = n_rows - 1; w >= 0; --w) {
-        uint32_t A = 0u, B = 0u;
-        if (w > 0) {
-            const uint32_t *row = bp + (int64_t)(w - 1) * Sp;
-            if (s_hi - lane >= 0) A = row[s_hi - lane];
-            if (s_hi - 32 - lane >= 0) B = row[s_hi - 32 - lane];
+    uint32_t q[LEAD][2];                                 // q[d]: band of row (w - 1 - d)
+    int qref[LEAD];
+    auto fetch = [&](int row, int ref, uint32_t (&w2)[2]) {
+        w2[0] = w2[1] = 0u;
+        if (row >= 0) {
+            const uint32_t *r = bp + (int64_t)row * Sp;
+            if (ref - lane >= 0) w2[0] = r[ref - lane];
+            if (ref - lane - 32 >= 0) w2[1] = r[ref - lane - 32];
         }
+    };
+    uint32_t W = (s_hi - lane >= 0) ? bp[(int64_t)(n_rows - 1) * Sp + (s_hi - lane)] : 0u;
+#pragma unroll
+    for (int dd = 0; dd < LEAD; ++dd) {
+        fetch(n_rows - 2 - dd, s_hi, q[dd]);
+        qref[dd] = s_hi;
+    }
+    for (int w = n_rows - 1; w >= 0; --w) {
+        uint32_t f[2];
+        fetch(w - 1 - LEAD, s_hi, f);                    // LEAD rows ahead, below the current state
+        const int fref = s_hi;
         int tt = (w == n_rows - 1) ? ((T - 1) & 15) : 15;
         int my_state = 0;
         while (tt >= 0) {
@@ -104,18 +121,33 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         }
         if (lane < 16 && 16 * w + lane < T) path_state[16 * w + lane] = my_state;
         if (w > 0) {
-            const int d = s_hi - s;                     // 0..32 states walked down in this row
-            const int src = (d + lane) & 31;
-            const uint32_t x = __shfl_sync(0xffffffffu, A, src);
-            const uint32_t y = __shfl_sync(0xffffffffu, B, src);
-            W = (d + lane < 32) ? x : y;
+            const int o = (qref[0] - s) + lane;         // offset of state (s - lane) inside band q[0]
+            if (qref[0] - s + 31 < 64) {                 // warp-uniform: the band covers it
+                const uint32_t x0 = __shfl_sync(0xffffffffu, q[0][0], o & 31);
+                const uint32_t x1 = __shfl_sync(0xffffffffu, q[0][1], o & 31);
+                W = (o < 32) ? x0 : x1;
+            } else {                                     // the path dropped > 32 states in LEAD rows
+                W = (s - lane >= 0) ? bp[(int64_t)(w - 1) * Sp + (s - lane)] : 0u;
+            }
             s_hi = s;
+#pragma unroll
+            for (int dd = 0; dd + 1 < LEAD; ++dd) {
+                q[dd][0] = q[dd + 1][0];
+                q[dd][1] = q[dd + 1][1];
+                qref[dd] = qref[dd + 1];
+            }
+            q[LEAD - 1][0] = f[0];
+            q[LEAD - 1][1] = f[1];
+            qref[LEAD - 1] = fref;
         }
     }
     if (n_seg > S) n_seg = S;                           // cannot happen with valid backpointers
     __syncwarp();
 
     // ---- phase 2: forward rescoring, frame confidence ----
+    // 32 frames per round: lanes gather the operands of their frame (software-pipelined: path
+    // states two rounds ahead, emissions one round ahead), then the f32/f64 chain itself runs once
+    // per frame, uniformly, over operands parked in shared memory.
     const float *emis = ws.emis + m.emis_off;
     const float2 *edge2 = ws.edge2 + m.edge_off;
     const double ratio = __ddiv_rn((double)T, (double)S);
@@ -123,51 +155,95 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     float4 *stage = stage_sm[warp];
     float *dpath = dpath_sm[warp];
     float d = 0.0f, cu = 0.0f, carry_d = 0.0f;          // dp_path[-1] := 0 (:286)
-    int carry_state = 0;
     double log_sum = 0.0;
-    for (int c0 = 0; c0 < T; c0 += 32) {
-        const int t = c0 + lane;
-        const bool valid = t < T;
-        const int st = valid ? path_state[t] : 0;
-        int sprev = __shfl_up_sync(0xffffffffu, st, 1);
-        if (lane == 0) sprev = (c0 == 0) ? st : carry_state;
-        carry_state = __shfl_sync(0xffffffffu, st, 31);
-        const int s0 = __shfl_sync(0xffffffffu, st, 0);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
+    const int n_rounds = (T + 31) >> 5;
+    auto load_state = [&](int round) {
+        const int t = round * 32 + lane;
+        return (round < n_rounds && t < T) ? path_state[t] : 0;
+    };
+    // flags: 1 = the path moved into this frame's state, 2 = that state is an id-0 (SP) state,
+    //        4 = frame past T (no-op), 8 = frame 0 (seed, :250-254)
+    auto gather = [&](int round, int st, int sprev) {
+        const int t = round * 32 + lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(4));
+        if (round < n_rounds && t < T) {
             const float *row = emis + (int64_t)t * Sp;
             const bool moved = (t > 0) && (sprev != st);
             const float2 ed = edge2[t];
             v.x = row[st];
             v.y = moved ? row[sprev] : v.x;
             v.z = moved ? ed.x : ed.y;
-            v.w = __int_as_float((moved ? 1 : 0) | ((ids[st] == 0) ? 2 : 0));
+            int fl = (moved ? 1 : 0) | ((ids[st] == 0) ? 2 : 0);
+            if (t == 0) {
+                const bool seeded = (st == 0) || (st == 1 && lead_sp);
+                v.x = seeded ? v.x : HFA_NEG_INF;
+                fl = 8;
+            }
+            v.w = __int_as_float(fl);
         }
-        stage[lane] = v;
+        return v;
+    };
+    int st_cur = load_state(0);
+    int st_nxt = load_state(1);
+    float4 v_cur = gather(0, st_cur, __shfl_up_sync(0xffffffffu, st_cur, 1));
+    for (int r = 0; r < n_rounds; ++r) {
+        // issue the loads of the following rounds before touching this round's results
+        const int st_nn = load_state(r + 2);
+        int sprev_n = __shfl_up_sync(0xffffffffu, st_nxt, 1);
+        const int last_cur = __shfl_sync(0xffffffffu, st_cur, 31);
+        if (lane == 0) sprev_n = last_cur;
+        const float4 v_nxt = gather(r + 1, st_nxt, sprev_n);
+
+        stage[lane] = v_cur;
+        // frames that are not a plain "stay" (moved / seed / past T): one bit per frame, uniform
+        const uint32_t special = __ballot_sync(0xffffffffu, (__float_as_int(v_cur.w) & 13) != 0);
         __syncwarp();
-        const int cnt = min(32, T - c0);
-        for (int j = 0; j < cnt; ++j) {
-            const float4 q = stage[j];
-            const int fl = __float_as_int(q.w);
-            if (c0 + j == 0) {
-                // :250-254 only state 0 (and state 1 behind a leading SP) are seeded
-                const bool seeded = (s0 == 0) || (s0 == 1 && lead_sp);
-                d = seeded ? q.x : HFA_NEG_INF;
-                cu = d;
-            } else {
+        // Runs of stay frames are a pure two-add chain (curr: running max, or 0 in an SP state, which
+        // is constant over a run); only the frames flagged in `special` take the branchy path.
+        int j = 0;
+        while (j < 32) {
+            if ((special >> j) & 1u) {
+                const float4 q = stage[j];
+                const int fl = __float_as_int(q.w);
                 if (fl & 1) {
                     d = hfa_advance(__fadd_rn(__fadd_rn(d, q.y), q.z), cu, ratio);
-                    cu = q.x;
-                } else {
-                    d = __fadd_rn(__fadd_rn(d, q.x), q.z);
-                    cu = fmaxf(cu, q.x);
+                    cu = (fl & 2) ? 0.0f : q.x;
+                } else if (fl & 8) {
+                    d = q.x;
+                    cu = d;
                 }
-                if (fl & 2) cu = 0.0f;
+                if (lane == 0) dpath[j] = d;
+                ++j;
+                continue;
             }
-            if (lane == 0) dpath[j] = d;
+            const uint32_t rest = special >> j;
+            const int run = rest ? (__ffs(rest) - 1) : (32 - j);
+            const bool sp_state = (__float_as_int(stage[j].w) & 2) != 0;
+            int k = 0;
+            for (; k + 4 <= run; k += 4) {
+                const float4 q0 = stage[j + k], q1 = stage[j + k + 1], q2 = stage[j + k + 2],
+                             q3 = stage[j + k + 3];
+                const float d0 = __fadd_rn(__fadd_rn(d, q0.x), q0.z);
+                const float d1 = __fadd_rn(__fadd_rn(d0, q1.x), q1.z);
+                const float d2 = __fadd_rn(__fadd_rn(d1, q2.x), q2.z);
+                d = __fadd_rn(__fadd_rn(d2, q3.x), q3.z);
+                cu = fmaxf(fmaxf(cu, q0.x), fmaxf(fmaxf(q1.x, q2.x), q3.x));
+                if (lane == 0) {
+                    dpath[j + k] = d0; dpath[j + k + 1] = d1; dpath[j + k + 2] = d2; dpath[j + k + 3] = d;
+                }
+            }
+            for (; k < run; ++k) {
+                const float4 q = stage[j + k];
+                d = __fadd_rn(__fadd_rn(d, q.x), q.z);
+                cu = fmaxf(cu, q.x);
+                if (lane == 0) dpath[j + k] = d;
+            }
+            if (sp_state) cu = 0.0f;
+            j += run;
         }
         __syncwarp();
-        if (valid) {
+        const int t = r * 32 + lane;
+        if (t < T) {
             const float cur = dpath[lane];
             const float prev = (lane == 0) ? carry_d : dpath[lane - 1];
             const float fc = expf(__fsub_rn(cur, prev));                 // :284-288
@@ -177,6 +253,9 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         }
         carry_d = d;
         __syncwarp();
+        st_cur = st_nxt;
+        st_nxt = st_nn;
+        v_cur = v_nxt;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) log_sum += __shfl_xor_sync(0xffffffffu, log_sum, o);

@@ -44,6 +44,7 @@ struct HfaWs {
     const int32_t *ids;          // concatenated phoneme ids
     const int32_t *order;        // bucket order lists (see plan)
     const int32_t *row_blocks;   // exclusive prefix of emission row-blocks per utterance [n+1]
+    const int32_t *block_utt;    // utterance of every 64-frame emission row-block [total blocks]
     HfaInput *inputs;
     float *emis;
     float2 *edge2;

@@ -4,16 +4,12 @@
 // by 1e9 in f32), :62-65 (log_softmax), :239 (gather columns by ph_seq_id), :68-71 (edge sigmoid,
 // rescale, clamp), :84 (edge_prob = clip(p[t] + p[t-1], 0, 1) in f64), :241-242 (f64 log -> f32).
 //
-// One CTA = 64 consecutive frames of one utterance.  Each warp owns 8 of those rows and handles
-// them two at a time (two independent rows of loads in flight): coalesced, strided-view-aware row
-// load -> masked max / sum(exp) by warp butterfly -> row parked in shared memory -> gather by the
-// phoneme ids (also in shared memory) -> coalesced float4 store of the [Sp] emission row.
-// Algorithmic HBM bytes per frame: V*sizeof(in) + 4 (edge logit) read, 4*Sp + 12 written.
+// One CTA = 64 consecutive frames of one utterance (see hfa_emission_block_kernel below).
+// Algorithmic HBM bytes per frame: V*sizeof(in) + sizeof(in) (edge logit) read, 4*S + 12 written.
 #include "hfa_common.cuh"
 
 #define HFA_EMIS_ROWS 64
 #define HFA_EMIS_WARPS 8
-#define HFA_EMIS_MAX_VPL 4        // register-staged path covers V <= 128; larger V streams via smem
 
 namespace {
 
@@ -28,18 +24,6 @@ __device__ __forceinline__ float warp_sum(float v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
-}
-
-// utterance that owns row-block `blk` (row_blocks is an exclusive prefix, [n+1])
-__device__ __forceinline__ int find_utt(const int32_t *row_blocks, int n, int blk)
-{
-    int lo = 0, hi = n;          // invariant: row_blocks[lo] <= blk < row_blocks[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (row_blocks[mid] <= blk) lo = mid;
-        else hi = mid;
-    }
-    return lo;
 }
 
 // clamp((sigmoid(x) - 0.1) / 0.8, 0, 1), all f32 (:68-71)
@@ -65,182 +49,14 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     return v;
 }
 
-// VPL = vocabulary entries per lane (V <= 32 * VPL) for the register-staged path, 0 = any V.
-// Shared memory: ids [sp_cap] (pads -> V), keep-mask words, row buffers [warps][rows][V + 1] whose
-// extra slot V holds -inf: a pad column gathers that slot and comes out as -inf without a select.
-template <typename TIn, int VPL>
-__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)
-hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
+// edge stream of one CTA's 64 frames, one thread per frame (:68-71,:84,:241-242)
+template <typename TIn>
+__device__ __forceinline__ void edge_block(const HfaWs &ws, const HfaUtt &m, const HfaInput &in,
+                                           int t_base, int tid)
 {
-    constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;                      // rows per warp
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t *ids_sm = reinterpret_cast<int32_t *>(smem_raw);                 // [sp_cap]
-    uint32_t *mask_sm = reinterpret_cast<uint32_t *>(ids_sm + sp_cap);       // [ceil(V/32)] keep bits
-    const int mask_words = (V + 31) >> 5;
-    float *rows_sm = reinterpret_cast<float *>(mask_sm + ((mask_words + 3) & ~3));
-    const int VS = V + 1;                                                    // row buffer stride
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = find_utt(ws.row_blocks, n_utt, blockIdx.x);
-    const HfaUtt m = ws.utt[u];
-    const HfaInput in = ws.inputs[u];
-    const int T = m.T, S = m.S, Sp = m.Sp;
-    const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
-    const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
-    float *g_out = ws.emis + m.emis_off;
-
-    // (1) every warp puts the loads of ALL its rows in flight before anything else.  Branch-free:
-    //     out-of-range lanes / rows read a clamped (valid) address and are replaced by -inf.
-    float x[RPW][VPL > 0 ? VPL : 1];
-    if constexpr (VPL > 0) {
-        const int64_t row_step = (int64_t)HFA_EMIS_WARPS * in.frame_st;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-            const int v = lane + 32 * q;
-            const TIn *col = frame + (int64_t)min(v, V - 1) * in.frame_sv;
-#pragma unroll
-            for (int r = 0; r < RPW; ++r) {
-                const int t = min(t_base + warp + HFA_EMIS_WARPS * r, T - 1);
-                const float xv = hfa_to_float<TIn>(col[(int64_t)t * in.frame_st]);
-                x[r][q] = (v < V) ? xv : HFA_NEG_INF;
-            }
-        }
-        (void)row_step;
-    }
-
-    // (2) phoneme ids and the keep-mask of this utterance -> shared memory
-    for (int w = tid; w < mask_words; w += blockDim.x) mask_sm[w] = (w == 0) ? 1u : 0u;  // id 0 (:39)
-    __syncthreads();
-    const int32_t *ids = ws.ids + m.seg_off;
-    for (int s = tid; s < Sp; s += blockDim.x) {
-        const int id = (s < S) ? ids[s] : V;
-        ids_sm[s] = id;
-        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
-    }
-    __syncthreads();
-
-    if constexpr (VPL > 0) {
-        // row buffers: stride 32*VPL+1 so every lane stores unconditionally; slots V.. hold the -inf
-        // of the out-of-range lanes, which is exactly the pad sentinel the gather needs at slot V
-        constexpr int RS = 32 * VPL + 1;
-        float *rowbuf = rows_sm + (size_t)warp * RPW * RS;
-        const uint32_t rowbuf_sa = hfa_smem_u32(rowbuf);
-        // per-lane constants: the 1e9 penalty of its vocabulary entries (:53) and the byte offsets
-        // of the (up to 8) row-buffer slots it gathers
-        float pen[VPL];
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-            const int v = min(lane + 32 * q, V - 1);
-            pen[q] = ((mask_sm[v >> 5] >> (v & 31)) & 1u) ? 0.0f : 1e9f;
-        }
-        uint32_t goff[2][4];
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int s4 = min(lane * 4 + 128 * it, Sp - 4);
-            const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
-            goff[it][0] = (uint32_t)id4.x * 4u; goff[it][1] = (uint32_t)id4.y * 4u;
-            goff[it][2] = (uint32_t)id4.z * 4u; goff[it][3] = (uint32_t)id4.w * 4u;
-        }
-
-        // (3) masked max / log-sum-exp of the 8 rows (independent chains), rows parked in smem
-        float mx[RPW], lse[RPW];
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            float mr = HFA_NEG_INF;
-#pragma unroll
-            for (int q = 0; q < VPL; ++q) {
-                x[r][q] = __fsub_rn(x[r][q], pen[q]);                        // :53 (x - 0 is exact)
-                mr = fmaxf(mr, x[r][q]);
-            }
-            mx[r] = warp_max(mr);
-        }
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            float sum = 0.0f;
-#pragma unroll
-            for (int q = 0; q < VPL; ++q) {
-                sum = __fadd_rn(sum, expf(__fsub_rn(x[r][q], mx[r])));       // exp(-inf) = 0 for v >= V
-                rowbuf[r * RS + lane + 32 * q] = x[r][q];
-            }
-            lse[r] = logf(warp_sum(sum));
-        }
-        __syncwarp();
-
-        // (4) gather by phoneme id and store: out[t][s] = (x[id[s]] - max) - lse
-        const int rows_here = min(RPW, (T - t_base - warp + HFA_EMIS_WARPS - 1) / HFA_EMIS_WARPS);
-        float *dst = g_out + (int64_t)(t_base + warp) * Sp + lane * 4;
-        const int dst_step = HFA_EMIS_WARPS * Sp;
-        const bool st0 = lane * 4 < Sp, st1 = lane * 4 + 128 < Sp;
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            if (r >= rows_here) break;                                       // warp-uniform
-            const uint32_t rb = rowbuf_sa + (uint32_t)(r * RS) * 4u;
-            float4 o0, o1;
-            o0.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][0]), mx[r]), lse[r]);
-            o0.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][1]), mx[r]), lse[r]);
-            o0.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][2]), mx[r]), lse[r]);
-            o0.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][3]), mx[r]), lse[r]);
-            if (st0) *reinterpret_cast<float4 *>(dst + r * dst_step) = o0;
-            if (Sp > 128) {                                                  // warp-uniform
-                o1.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][0]), mx[r]), lse[r]);
-                o1.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][1]), mx[r]), lse[r]);
-                o1.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][2]), mx[r]), lse[r]);
-                o1.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][3]), mx[r]), lse[r]);
-                if (st1) *reinterpret_cast<float4 *>(dst + r * dst_step + 128) = o1;
-            }
-        }
-        if (Sp > 256) {                                                      // long phoneme sequences
-            for (int r = 0; r < rows_here; ++r) {
-                for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {
-                    const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
-                    float4 o;
-                    o.x = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.x], mx[r]), lse[r]);
-                    o.y = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.y], mx[r]), lse[r]);
-                    o.z = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.z], mx[r]), lse[r]);
-                    o.w = __fsub_rn(__fsub_rn(rowbuf[r * RS + id4.w], mx[r]), lse[r]);
-                    *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
-                }
-            }
-        }
-    } else {
-        // wide vocabularies: one row at a time through the shared-memory row buffer
-        float *rowbuf = rows_sm + (size_t)warp * VS;
-        if (lane == 0) rowbuf[V] = HFA_NEG_INF;
-        __syncwarp();
-        for (int j = 0; j < RPW; ++j) {
-            const int t = t_base + warp + HFA_EMIS_WARPS * j;
-            if (t >= T) continue;
-            const TIn *src = frame + (int64_t)t * in.frame_st;
-            float mr = HFA_NEG_INF;
-            for (int v = lane; v < V; v += 32) {
-                float xv = hfa_to_float<TIn>(src[(int64_t)v * in.frame_sv]);
-                if (!((mask_sm[v >> 5] >> (v & 31)) & 1u)) xv = __fsub_rn(xv, 1e9f);
-                rowbuf[v] = xv;
-                mr = fmaxf(mr, xv);
-            }
-            mr = warp_max(mr);
-            float sum = 0.0f;
-            for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, expf(__fsub_rn(rowbuf[v], mr)));
-            const float l = logf(warp_sum(sum));
-            __syncwarp();
-            float *dst = g_out + (int64_t)t * Sp;
-            for (int s4 = lane * 4; s4 < Sp; s4 += 128) {
-                const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
-                float4 o;
-                o.x = __fsub_rn(__fsub_rn(rowbuf[id4.x], mr), l);
-                o.y = __fsub_rn(__fsub_rn(rowbuf[id4.y], mr), l);
-                o.z = __fsub_rn(__fsub_rn(rowbuf[id4.z], mr), l);
-                o.w = __fsub_rn(__fsub_rn(rowbuf[id4.w], mr), l);
-                *reinterpret_cast<float4 *>(dst + s4) = o;
-            }
-            __syncwarp();
-        }
-    }
-
-    // edge stream of this CTA's 64 frames, one thread per frame
     if (tid < HFA_EMIS_ROWS) {
         const int t = t_base + tid;
-        if (t < T) {
+        if (t < m.T) {
             const TIn *edge = reinterpret_cast<const TIn *>(in.edge);
             const float p = edge_pred(hfa_to_float<TIn>(edge[(int64_t)t * in.edge_st]));
             const float pp =
@@ -253,6 +69,225 @@ hfa_emission_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Main emission kernel (V <= HFA_EMIS_BLOCK_MAX_V).  One CTA = 64 frames of one utterance:
+//   A. the 8 warps load the 64 x V logits block coalesced (strided-view aware) into shared memory,
+//      row stride VP odd -> a thread walking one row and a warp walking a column are conflict-free;
+//   B. phoneme ids -> smem (pads -> slot V, which holds -inf), keep-mask, compacted list of the kept
+//      vocabulary ids (ids of ph_seq U {0}, alignment_decoder.py:37-39);
+//   C. normaliser: 4 threads per frame walk the KEPT ids only (max, then sum of exp) and combine
+//      with two shuffles -- no 32-lane butterfly per row, no exp for the masked entries (the
+//      reference pushes those down by 1e9, so their exp is exactly 0 and they never win the max
+//      for |logit| < 5e8, :53);
+//   D. each warp gathers its 8 rows by phoneme id (byte offsets held in registers) and stores the
+//      [Sp] emission rows as float4: out = (x[id] - max) - log(sum), the reference's order (:63).
+// ---------------------------------------------------------------------------------------------
+#define HFA_EMIS_BLOCK_MAX_V 255
+
+template <typename TIn>
+__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32, 5)
+hfa_emission_block_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
+{
+    constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;                      // rows per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int VP = (V + 1) | 1;                                              // odd, >= V + 1
+    const int mask_words = (V + 31) >> 5;
+    int32_t *ids_sm = reinterpret_cast<int32_t *>(smem_raw);                 // [sp_cap]
+    uint32_t *mask_sm = reinterpret_cast<uint32_t *>(ids_sm + sp_cap);       // [8]
+    int32_t *kept_sm = reinterpret_cast<int32_t *>(mask_sm + 8);             // [256]
+    float2 *stat_sm = reinterpret_cast<float2 *>(kept_sm + 256);             // [64] {max, lse}
+    float *xs = reinterpret_cast<float *>(stat_sm + HFA_EMIS_ROWS);          // [64][VP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = ws.block_utt[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    const HfaInput in = ws.inputs[u];
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+    const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
+
+    // A. logits block -> smem (rows past T re-read row T-1: valid memory, results never stored)
+    {
+        const TIn *rowp[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+            rowp[r] = frame + (int64_t)min(t_base + warp + HFA_EMIS_WARPS * r, T - 1) * in.frame_st +
+                      (int64_t)lane * in.frame_sv;
+        const int64_t vstep = 32 * in.frame_sv;
+        float *xw = xs + warp * VP + lane;
+        for (int v = lane; v < V; v += 32) {
+            float xv[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                xv[r] = hfa_to_float<TIn>(*rowp[r]);
+                rowp[r] += vstep;
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) xw[r * HFA_EMIS_WARPS * VP] = xv[r];
+            xw += 32;
+        }
+    }
+    if (lane < RPW) xs[(warp + HFA_EMIS_WARPS * lane) * VP + V] = HFA_NEG_INF;   // pad sentinel
+
+    // B. ids, keep mask, kept list
+    if (tid < 8) mask_sm[tid] = (tid == 0) ? 1u : 0u;                        // id 0 always kept (:39)
+    __syncthreads();
+    const int32_t *ids = ws.ids + m.seg_off;
+    for (int s = tid; s < Sp; s += blockDim.x) {
+        const int id = (s < S) ? ids[s] : V;
+        ids_sm[s] = id;
+        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+    }
+    __syncthreads();
+    int n_kept = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n_kept += (w < mask_words) ? __popc(mask_sm[w]) : 0;
+    if (tid < V && ((mask_sm[tid >> 5] >> (tid & 31)) & 1u)) {
+        int pos = __popc(mask_sm[tid >> 5] & ((1u << (tid & 31)) - 1u));
+        for (int w = 0; w < (tid >> 5); ++w) pos += __popc(mask_sm[w]);
+        kept_sm[pos] = tid;
+    }
+    __syncthreads();
+
+    // C. normaliser: thread -> (row = tid / 4, part = tid % 4)
+    {
+        const float *row = xs + (tid >> 2) * VP;
+        const int part = tid & 3;
+        float mx = HFA_NEG_INF;
+        for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, row[kept_sm[k]]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.0f;
+        for (int k = part; k < n_kept; k += 4) sum = __fadd_rn(sum, expf(__fsub_rn(row[kept_sm[k]], mx)));
+        sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+        sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+        if (part == 0) stat_sm[tid >> 2] = make_float2(mx, logf(sum));
+    }
+    __syncthreads();
+
+    // D. gather by phoneme id and store
+    {
+        uint32_t goff[2][4];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int s4 = min(lane * 4 + 128 * it, Sp - 4);
+            const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+            goff[it][0] = (uint32_t)id4.x * 4u; goff[it][1] = (uint32_t)id4.y * 4u;
+            goff[it][2] = (uint32_t)id4.z * 4u; goff[it][3] = (uint32_t)id4.w * 4u;
+        }
+        const uint32_t xs_sa = hfa_smem_u32(xs);
+        const int rows_here = min(RPW, (T - t_base - warp + HFA_EMIS_WARPS - 1) / HFA_EMIS_WARPS);
+        float *dst = ws.emis + m.emis_off + (int64_t)(t_base + warp) * Sp + lane * 4;
+        const int dst_step = HFA_EMIS_WARPS * Sp;
+        const bool st0 = lane * 4 < Sp, st1 = lane * 4 + 128 < Sp;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            if (r >= rows_here) break;                                       // warp-uniform
+            const int rr = warp + HFA_EMIS_WARPS * r;
+            const float2 st = stat_sm[rr];
+            const uint32_t rb = xs_sa + (uint32_t)(rr * VP) * 4u;
+            float4 o;
+            o.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][0]), st.x), st.y);
+            o.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][1]), st.x), st.y);
+            o.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][2]), st.x), st.y);
+            o.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[0][3]), st.x), st.y);
+            if (st0) *reinterpret_cast<float4 *>(dst + r * dst_step) = o;
+            if (Sp > 128) {                                                  // warp-uniform
+                o.x = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][0]), st.x), st.y);
+                o.y = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][1]), st.x), st.y);
+                o.z = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][2]), st.x), st.y);
+                o.w = __fsub_rn(__fsub_rn(lds_f32(rb + goff[1][3]), st.x), st.y);
+                if (st1) *reinterpret_cast<float4 *>(dst + r * dst_step + 128) = o;
+            }
+        }
+        if (Sp > 256) {                                                      // long phoneme sequences
+            for (int r = 0; r < rows_here; ++r) {
+                const int rr = warp + HFA_EMIS_WARPS * r;
+                const float2 st = stat_sm[rr];
+                for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {
+                    const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+                    float4 o;
+                    o.x = __fsub_rn(__fsub_rn(xs[rr * VP + id4.x], st.x), st.y);
+                    o.y = __fsub_rn(__fsub_rn(xs[rr * VP + id4.y], st.x), st.y);
+                    o.z = __fsub_rn(__fsub_rn(xs[rr * VP + id4.z], st.x), st.y);
+                    o.w = __fsub_rn(__fsub_rn(xs[rr * VP + id4.w], st.x), st.y);
+                    *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
+                }
+            }
+        }
+    }
+    edge_block<TIn>(ws, m, in, t_base, tid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide vocabularies (V > HFA_EMIS_BLOCK_MAX_V): one warp per row, rows streamed through a per-warp
+// shared-memory buffer, full masked softmax exactly as the reference spells it.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)
+hfa_emission_wide_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
+{
+    constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *ids_sm = reinterpret_cast<int32_t *>(smem_raw);                 // [sp_cap]
+    uint32_t *mask_sm = reinterpret_cast<uint32_t *>(ids_sm + sp_cap);       // [ceil(V/32)] keep bits
+    const int mask_words = (V + 31) >> 5;
+    float *rows_sm = reinterpret_cast<float *>(mask_sm + ((mask_words + 3) & ~3));
+    const int VS = V + 1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = ws.block_utt[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    const HfaInput in = ws.inputs[u];
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+    const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
+    float *g_out = ws.emis + m.emis_off;
+
+    for (int w = tid; w < mask_words; w += blockDim.x) mask_sm[w] = (w == 0) ? 1u : 0u;  // id 0 (:39)
+    __syncthreads();
+    const int32_t *ids = ws.ids + m.seg_off;
+    for (int s = tid; s < Sp; s += blockDim.x) {
+        const int id = (s < S) ? ids[s] : V;
+        ids_sm[s] = id;
+        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+    }
+    __syncthreads();
+
+    float *rowbuf = rows_sm + (size_t)warp * VS;
+    if (lane == 0) rowbuf[V] = HFA_NEG_INF;
+    __syncwarp();
+    for (int j = 0; j < RPW; ++j) {
+        const int t = t_base + warp + HFA_EMIS_WARPS * j;
+        if (t >= T) continue;
+        const TIn *src = frame + (int64_t)t * in.frame_st;
+        float mr = HFA_NEG_INF;
+        for (int v = lane; v < V; v += 32) {
+            float xv = hfa_to_float<TIn>(src[(int64_t)v * in.frame_sv]);
+            if (!((mask_sm[v >> 5] >> (v & 31)) & 1u)) xv = __fsub_rn(xv, 1e9f);          // :53
+            rowbuf[v] = xv;
+            mr = fmaxf(mr, xv);
+        }
+        mr = warp_max(mr);
+        float sum = 0.0f;
+        for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, expf(__fsub_rn(rowbuf[v], mr)));
+        const float l = logf(warp_sum(sum));
+        __syncwarp();
+        float *dst = g_out + (int64_t)t * Sp;
+        for (int s4 = lane * 4; s4 < Sp; s4 += 128) {
+            const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+            float4 o;
+            o.x = __fsub_rn(__fsub_rn(rowbuf[id4.x], mr), l);
+            o.y = __fsub_rn(__fsub_rn(rowbuf[id4.y], mr), l);
+            o.z = __fsub_rn(__fsub_rn(rowbuf[id4.z], mr), l);
+            o.w = __fsub_rn(__fsub_rn(rowbuf[id4.w], mr), l);
+            *reinterpret_cast<float4 *>(dst + s4) = o;
+        }
+        __syncwarp();
+    }
+    edge_block<TIn>(ws, m, in, t_base, tid);
+}
+
 // the reference's forward_pass inputs given directly (dense ragged), repacked into the workspace
 __global__ void __launch_bounds__(256)
 hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
@@ -260,7 +295,7 @@ hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
                 const float *__restrict__ edge_pred_in)
 {
     const int tid = threadIdx.x;
-    const int u = find_utt(ws.row_blocks, n_utt, blockIdx.x);
+    const int u = ws.block_utt[blockIdx.x];
     const HfaUtt m = ws.utt[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
@@ -284,26 +319,26 @@ template <typename TIn>
 static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_sp)
 {
     const int V = c.vocab;
-    const int vpl = (V + 31) / 32;
-    const int mask_words = (V + 31) >> 5;
-    const size_t rows = (vpl <= HFA_EMIS_MAX_VPL) ? (size_t)HFA_EMIS_ROWS : (size_t)HFA_EMIS_WARPS;
-    const size_t stride = (vpl <= HFA_EMIS_MAX_VPL) ? (size_t)(32 * vpl + 1) : (size_t)(V + 1);
-    const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 + rows * stride * 4;
     cudaError_t e;
-#define HFA_EMIS_LAUNCH(VPL)                                                                       \
-    e = cudaFuncSetAttribute(hfa_emission_kernel<TIn, VPL>,                                        \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-    if (e != cudaSuccess) return e;                                                                \
-    hfa_emission_kernel<TIn, VPL><<<blocks, HFA_EMIS_WARPS * 32, smem, c.stream>>>(c.ws, c.n_utt,  \
-                                                                                  V, max_sp)
-    switch (vpl <= HFA_EMIS_MAX_VPL ? vpl : 0) {
-        case 1: HFA_EMIS_LAUNCH(1); break;
-        case 2: HFA_EMIS_LAUNCH(2); break;
-        case 3: HFA_EMIS_LAUNCH(3); break;
-        case 4: HFA_EMIS_LAUNCH(4); break;
-        default: HFA_EMIS_LAUNCH(0); break;
+    if (V <= HFA_EMIS_BLOCK_MAX_V) {
+        const int VP = (V + 1) | 1;
+        const size_t smem = (size_t)max_sp * 4 + 8 * 4 + 256 * 4 + HFA_EMIS_ROWS * 8 +
+                            (size_t)HFA_EMIS_ROWS * VP * 4;
+        e = cudaFuncSetAttribute(hfa_emission_block_kernel<TIn>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_emission_block_kernel<TIn><<<blocks, HFA_EMIS_WARPS * 32, smem, c.stream>>>(c.ws, c.n_utt,
+                                                                                    V, max_sp);
+    } else {
+        const int mask_words = (V + 31) >> 5;
+        const size_t smem = (size_t)max_sp * 4 + (size_t)((mask_words + 3) & ~3) * 4 +
+                            (size_t)HFA_EMIS_WARPS * (V + 1) * 4;
+        e = cudaFuncSetAttribute(hfa_emission_wide_kernel<TIn>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_emission_wide_kernel<TIn><<<blocks, HFA_EMIS_WARPS * 32, smem, c.stream>>>(c.ws, c.n_utt,
+                                                                                   V, max_sp);
     }
-#undef HFA_EMIS_LAUNCH
     return cudaGetLastError();
 }
 
