@@ -19,7 +19,7 @@ cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *orde
                                float *dp_dump);
 cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
                                    float *dp_dump);
-cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp,
+cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype);
 cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const float *prob_log,
@@ -93,6 +93,7 @@ struct hfa_plan {
     int32_t class_count[HFA_NUM_CLASSES + 1] = {0};
     int32_t cta_max_sp = 0, max_sp = 4;
     int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
+    int32_t lat_begin = 0, lat_count = 0, lat_max_sp = 0;            // small-batch latency routing
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
     std::vector<int32_t> block_utt;            // [row_blocks[n]]
@@ -249,6 +250,23 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             p->order.insert(p->order.end(), lists[c].begin(), lists[c].end());
             all.insert(all.end(), lists[c].begin(), lists[c].end());
         }
+        // Experimental routing (HFA_LATENCY_MODE=1, off by default): utterances with more than 2
+        // states per lane go to the multi-warp kernel (2 states per thread, ceil(Sp/64) warps).
+        // Measured on B200 (config 2) the per-frame barrier costs more than the shorter per-warp
+        // instruction stream saves (0.317 ms vs 0.271 ms for the DP stage), so it stays opt-in; the
+        // parity tests run both routings.
+        bool latency = false;
+        if (const char *e = std::getenv("HFA_LATENCY_MODE")) latency = (e[0] == '1');
+        std::vector<int32_t> lat;
+        if (latency) {
+            for (int c = 2; c < HFA_NUM_CLASSES; ++c) {
+                lat.insert(lat.end(), lists[c].begin(), lists[c].end());
+                for (int32_t b : lists[c]) p->lat_max_sp = std::max(p->lat_max_sp, p->utt[b].Sp);
+                lists[c].clear();
+                p->class_count[c] = 0;
+            }
+            std::sort(lat.begin(), lat.end(), by_len);
+        }
         // merged warp-kernel list: longest expected run time first (frames x per-frame cost, which
         // grows with the states per lane)
         std::vector<int32_t> warp_all;
@@ -262,6 +280,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->warp_all_begin = (int32_t)p->order.size();
         p->warp_all_count = (int32_t)warp_all.size();
         p->order.insert(p->order.end(), warp_all.begin(), warp_all.end());
+        p->lat_begin = (int32_t)p->order.size();
+        p->lat_count = (int32_t)lat.size();
+        p->order.insert(p->order.end(), lat.begin(), lat.end());
         std::sort(all.begin(), all.end(), by_len);
         p->bt_begin = (int32_t)p->order.size();
         p->order.insert(p->order.end(), all.begin(), all.end());
@@ -455,7 +476,7 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
     const int n_cta = p->class_count[HFA_NUM_CLASSES];
     // launches of this call: (merged ? 1 : one per class) + the CTA-per-utterance kernel
     struct Item { int k; const int32_t *order; int n; };
-    Item items[HFA_NUM_CLASSES + 2];
+    Item items[HFA_NUM_CLASSES + 3];
     int n_items = 0;
     if (mode == 0) {
         if (p->warp_all_count > 0)
@@ -465,6 +486,7 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             if (p->class_count[k] > 0)
                 items[n_items++] = {k + 1, c.ws.order + p->class_begin[k], p->class_count[k]};
     }
+    if (p->lat_count > 0) items[n_items++] = {-2, c.ws.order + p->lat_begin, p->lat_count};
     if (n_cta > 0) items[n_items++] = {-1, c.ws.order + p->class_begin[HFA_NUM_CLASSES], n_cta};
     if (n_items == 0) return HFA_OK;
 
@@ -489,8 +511,10 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             e = hfa_launch_dp_warp_any(c, p->warp_max_k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k > 0)
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
+        else if (items[it].k == -2)
+            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else
-            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->cta_max_sp, dp_dump);
+            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->cta_max_sp, HFA_CTA_K, dp_dump);
         if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: kernel launch");
         g_launches += 1;
         if (side) {

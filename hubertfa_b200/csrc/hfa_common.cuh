@@ -1,11 +1,11 @@
 // hfa_common.cuh -- shared declarations of the sm_100a forced-alignment kernels.
 //
-// Data layout in HBM (one "plan" = one ragged batch, see hfa_plan.cu):
-//   emissions  emis[utt][t][s]  f32, row stride Sp = round_up(S, 4) so every row and every 16-frame
+// Data layout in HBM (one "plan" = one ragged batch, see hfa_api.cu):
+//   emissions  emis[utt][t][s]  f32, row stride Sp = round_up(S, 4) so every row and every 8-frame
 //              tile starts 16-byte aligned -> a tile is ONE contiguous 1-D bulk (TMA) copy.
 //              Columns S..Sp-1 hold -inf (inert pad states to the right of the last real state).
 //   edge pair  edge2[utt][t]    {log(edge_prob+1e-6), log(1-edge_prob+1e-6)} f32x2, frame count
-//              padded to a multiple of 16 per utterance so every tile copy is 128 bytes.
+//              padded to a multiple of 16 per utterance so every tile copy is 64 / 128 bytes.
 //   edge_p     edge_p[utt][t]   f32 clamp((sigmoid-0.1)/0.8) (same padded indexing as edge2).
 //   backptr    bp[utt][t/16][s] u32: bit tt = "advanced by one" and bit 16+tt = "jumped over an
 //              SP" for frame t = 16*(t/16)+tt  (2 bits per DP cell, written once per 16 frames).

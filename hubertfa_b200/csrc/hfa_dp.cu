@@ -359,12 +359,11 @@ hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int s
 // ---------------------------------------------------------------------------------------------
 constexpr int HFA_CTA_STAGES = 3;
 
-template <int NT>
+template <int K, int NT>
 __global__ void __launch_bounds__(NT)
 hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int stage_floats,
                   float *__restrict__ dp_dump)
 {
-    constexpr int K = HFA_CTA_K;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [stages x stage_floats f32][stages x 16 float2][stages mbarriers][2 x 32 float2 exchange]
     float *tile0 = reinterpret_cast<float *>(smem_raw);
@@ -376,6 +375,11 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
     const int u = order[blockIdx.x];
     const HfaUtt m = ws.utt[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
+    // the launch is sized for the longest phoneme sequence of the list: warps that own no state of
+    // THIS utterance leave, the rest synchronise on a barrier sized to the warps that stay
+    const int n_active = (((Sp + K - 1) / K) + 31) & ~31;
+    if (tid >= n_active) return;
+    auto cta_sync = [&]() { asm volatile("bar.sync 0, %0;" ::"r"(n_active) : "memory"); };
     const int first = tid * K;
     const int n_tiles = (T + tile_t - 1) / tile_t;
     const float *g_emis = ws.emis + m.emis_off;
@@ -405,7 +409,7 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
     float jump_cap[K];
     hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
     const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
-    __syncthreads();
+    cta_sync();
 
     float dp[K], cu[K];
     uint32_t bits[K];
@@ -452,7 +456,7 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
             float up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
             float2 *slot = xch + (t & 1) * 32;
             if (lane == 31) slot[warp] = make_float2(adv[K - 1], adv[K - 2]);
-            __syncthreads();
+            cta_sync();
             if (lane == 0) {
                 if (warp == 0) {
                     up1 = HFA_NEG_INF;
@@ -480,7 +484,7 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
         }
         // Every thread has read its last row of stage `st` before the barrier of that frame (or,
         // for a tile that only holds frame 0, before this point): one more barrier frees the stage.
-        __syncthreads();
+        cta_sync();
         if (tid == 0 && i + HFA_CTA_STAGES < n_tiles) issue(i + HFA_CTA_STAGES);
     }
     if (T == 1) hfa_store_bits<K>(g_bp + first, bits, first, Sp);   // row 0 word (all zero)
@@ -566,14 +570,17 @@ cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *orde
     }
 }
 
-// all utterances of the CTA class share one launch; max_sp = largest padded S among them
-cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp,
+// all utterances of a CTA-per-utterance list share one launch; max_sp = largest padded S among them,
+// k = states per thread (8: long phoneme sequences; 2: the small-batch "latency" routing, where an
+// utterance gets ceil(Sp/64) warps instead of one so that its serial chain issues fewer
+// instructions per frame)
+cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    int threads = (max_sp + HFA_CTA_K - 1) / HFA_CTA_K;
+    int threads = (max_sp + k - 1) / k;
     threads = ((threads + 31) / 32) * 32;
-    if (threads > 1024) return cudaErrorInvalidValue;
+    if (threads > 1024 || (k != 2 && k != HFA_CTA_K)) return cudaErrorInvalidValue;
     // frames per stage: largest power of two <= 16 whose stage stays under ~64 KB
     int tile_t = HFA_TILE_T;
     while (tile_t > 1 && (size_t)tile_t * max_sp * sizeof(float) > 64 * 1024) tile_t >>= 1;
@@ -582,14 +589,18 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
                         HFA_CTA_STAGES * HFA_TILE_T * sizeof(float2) +
                         HFA_CTA_STAGES * sizeof(uint64_t) + 2 * 32 * sizeof(float2);
     cudaError_t e;
-#define HFA_CTA_LAUNCH(NT)                                                                         \
-    e = cudaFuncSetAttribute(hfa_dp_cta_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                             (int)smem);                                                           \
+#define HFA_CTA_LAUNCH(KK, NT)                                                                     \
+    e = cudaFuncSetAttribute(hfa_dp_cta_kernel<KK, NT>,                                            \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
     if (e != cudaSuccess) return e;                                                                \
-    hfa_dp_cta_kernel<NT><<<n, threads, smem, c.stream>>>(c.ws, order, tile_t, stage_floats, dp_dump)
-    if (threads <= 256) { HFA_CTA_LAUNCH(256); }
-    else if (threads <= 512) { HFA_CTA_LAUNCH(512); }
-    else { HFA_CTA_LAUNCH(1024); }
+    hfa_dp_cta_kernel<KK, NT><<<n, threads, smem, c.stream>>>(c.ws, order, tile_t, stage_floats,   \
+                                                             dp_dump)
+    if (k == 2) {
+        if (threads > 128) return cudaErrorInvalidValue;
+        HFA_CTA_LAUNCH(2, 128);
+    } else if (threads <= 256) { HFA_CTA_LAUNCH(HFA_CTA_K, 256); }
+    else if (threads <= 512) { HFA_CTA_LAUNCH(HFA_CTA_K, 512); }
+    else { HFA_CTA_LAUNCH(HFA_CTA_K, 1024); }
 #undef HFA_CTA_LAUNCH
     return cudaGetLastError();
 }

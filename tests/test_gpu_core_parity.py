@@ -11,7 +11,15 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-def test_golden_cases_one_batch(golden):
+@pytest.fixture(params=["0", "1"], ids=["warp-per-utterance", "latency-routing"])
+def routing(request, monkeypatch):
+    """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes),
+    1 = utterances with > 64 states go to the multi-warp kernel (the small-batch default)."""
+    monkeypatch.setenv("HFA_LATENCY_MODE", request.param)
+    return request.param
+
+
+def test_golden_cases_one_batch(golden, routing):
     """All golden cases in ONE ragged batch: every state class incl. the CTA kernel, T=1, S=1,
     infeasible alignments.  Paths must equal the reference's, scores the oracle's bit for bit."""
     import torch
@@ -44,7 +52,7 @@ SHAPES = [  # (T, S, style) -- every K class of the warp kernel, tile-boundary T
 ]
 
 
-def test_random_shapes_all_classes():
+def test_random_shapes_all_classes(routing):
     ins = [synth_core_inputs(T, S, 63, 4000 + i, style, planted=bool(i % 2))
            for i, (T, S, style) in enumerate(SHAPES)]
     out = run_core_gpu([x["ids"] for x in ins], [x["prob_log"] for x in ins], [x["el"] for x in ins],
@@ -56,7 +64,7 @@ def test_random_shapes_all_classes():
             raise AssertionError(f"shape {shp}: {e}") from e
 
 
-def test_ties_go_to_the_earlier_candidate():
+def test_ties_go_to_the_earlier_candidate(routing):
     """Constant emissions and edge logs make stay/advance/skip tie everywhere: the strict '>' scan
     (alignment_decoder.py:210-218) must be reproduced exactly."""
     T, S = 64, 21

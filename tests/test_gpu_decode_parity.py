@@ -220,3 +220,29 @@ def test_random_logits_tier2_protocol():
             differ += 1
     print(f"tier-2: {differ} of {len(items)} paths differ from the CPU-torch reference (all explained)")
     assert differ <= 3
+
+
+def test_host_pipeline_matches_decode_batch():
+    """HostBatchAligner (chunked upload overlapped with the kernels) returns the same segments, in
+    the caller's utterance order, as decode_batch on device-resident logits."""
+    from hubertfa_b200.pipeline import BufferPool, HostBatchAligner
+    V = 63
+    T, S = synth.sample_shapes(40, seed=21, min_s=1, max_s=10, s_lo=4, s_hi=140)
+    vocab, items = synth.make_batch(T, S, V, seed=21, planted=True)
+    head = torch.cat([torch.cat([it["edge"][0][:, None], torch.zeros(int(t), 1), it["frame"][0]], dim=1)
+                      for it, t in zip(items, T)]).pin_memory()
+    ids_cat = np.concatenate([it["ids"] for it in items])
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    ref = dec.decode_batch([it["frame"].cuda() for it in items], [it["edge"].cuda() for it in items],
+                           [it["ph_seq"] for it in items])
+    pool = BufferPool(torch.device("cuda"))
+    for n_chunks in (1, 3, 4, 64):
+        for _ in range(2):                      # second pass reuses the pooled buffers
+            al = HostBatchAligner(T, S, ids_cat, V, dec.frame_length, V + 2, n_chunks=n_chunks, pool=pool)
+            out = al.run(head)
+            assert (out["status"] == 0).all()
+            for b in range(len(items)):
+                idx, tim, iv = al.segments(out, b)
+                ridx, rtim, riv = ref.segments(b)
+                assert np.array_equal(idx, ridx) and np.array_equal(tim, rtim) and np.array_equal(iv, riv)
+                assert bits(out["total_conf"][b]) == bits(ref.total_confidence[b])
