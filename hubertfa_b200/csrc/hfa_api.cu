@@ -21,7 +21,9 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
                                    float *dp_dump);
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
-cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype);
+cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
+                                int64_t max_row_stride, int *n_launched);
+cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype);
 cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const float *prob_log,
                             const float *edge_log, const float *not_edge_log,
                             const float *edge_pred);
@@ -104,6 +106,9 @@ struct hfa_plan {
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
             o_last = 0, ws_bytes = 0;
     std::vector<unsigned char> head;           // host image of the head (without inputs)
+    // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
+    // aligned base pointers and positive row strides of at most this many elements (TMA path)
+    mutable int64_t max_row_stride = 0;
     HfaResultLayout res{};
 };
 
@@ -409,9 +414,17 @@ int hfa_set_inputs(const hfa_plan *p, void *workspace, const void *const *frame_
     if (!frame_ptrs || !frame_stride_t || !frame_stride_v || !edge_ptrs || !edge_stride)
         return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL input table");
     std::vector<HfaInput> in((size_t)p->n_utt);
+    int64_t row_stride = 0;
+    bool contiguous = true;
     for (int32_t b = 0; b < p->n_utt; ++b) {
         if (p->utt[b].status == 0 && (!frame_ptrs[b] || !edge_ptrs[b]))
             return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL logits pointer for utterance %d", b);
+        if (p->utt[b].status == 0) {
+            if (frame_stride_v[b] != 1 || frame_stride_t[b] < p->vocab ||
+                (reinterpret_cast<uintptr_t>(frame_ptrs[b]) & 3u))
+                contiguous = false;
+            row_stride = std::max(row_stride, frame_stride_t[b]);
+        }
         in[b].frame = frame_ptrs[b];
         in[b].edge = edge_ptrs[b];
         in[b].frame_st = frame_stride_t[b];
@@ -423,6 +436,7 @@ int hfa_set_inputs(const hfa_plan *p, void *workspace, const void *const *frame_
     cudaError_t e = cudaMemcpyAsync(c.ws.inputs, in.data(), in.size() * sizeof(HfaInput),
                                     cudaMemcpyHostToDevice, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_set_inputs: input table upload");
+    p->max_row_stride = contiguous ? row_stride : 0;
     return HFA_OK;
 }
 
@@ -432,9 +446,32 @@ int hfa_emission(const hfa_plan *p, void *workspace, int32_t dtype, void *stream
     if (p->n_utt == 0 || p->total_frames == 0) return HFA_OK;
     if (dtype < 0 || dtype > 2) return fail(HFA_ERR_ARG, "hfa_emission: bad dtype %d", dtype);
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
-    cudaError_t e = hfa_launch_emission(c, p->row_blocks[p->n_utt], p->max_sp, dtype);
+    static const bool no_tma = [] { const char *v = std::getenv("HFA_EMISSION_NO_TMA"); return v && v[0] == '1'; }();
+    const int64_t row_stride = no_tma ? 0 : p->max_row_stride;
+    // The persistent (TMA) emission kernel leaves the edge stream to its own small kernel, forked
+    // onto a side stream so that the two overlap and joined before anything downstream.  The fork
+    // point has to be recorded BEFORE the emission launch is queued.
+    HfaSideStreams *ss = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (row_stride > 0) {
+        ss = side_streams();
+        if (!ss) return fail(HFA_ERR_CUDA, "hfa_emission: cannot create side streams");
+        e = cudaEventRecord(ss->fork, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_emission: fork");
+    }
+    int n_launched = 0;
+    e = hfa_launch_emission(c, p->row_blocks[p->n_utt], p->max_sp, dtype, row_stride, &n_launched);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_emission: launch");
-    g_launches += 1;
+    if (n_launched == 2) {
+        HfaLaunchCtx cs = c;
+        cs.stream = ss->stream[HFA_NUM_CLASSES - 1];
+        e = cudaStreamWaitEvent(cs.stream, ss->fork, 0);
+        if (e == cudaSuccess) e = hfa_launch_edge(cs, p->row_blocks[p->n_utt], dtype);
+        if (e == cudaSuccess) e = cudaEventRecord(ss->join[HFA_NUM_CLASSES - 1], cs.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, ss->join[HFA_NUM_CLASSES - 1], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_emission: edge kernel");
+    }
+    g_launches += n_launched;
     return HFA_OK;
 }
 

@@ -219,6 +219,188 @@ hfa_emission_block_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     edge_block<TIn>(ws, m, in, t_base, tid);
 }
 
+// The edge stream on its own (one thread per frame), used next to the persistent emission kernel:
+// its two f64 logs per frame are ~250 instructions for a quarter of a CTA and would otherwise sit
+// between that kernel's barriers.
+template <typename TIn>
+__global__ void __launch_bounds__(HFA_EMIS_ROWS)
+hfa_edge_kernel(HfaWs ws)
+{
+    const int u = ws.block_utt[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    const HfaInput in = ws.inputs[u];
+    edge_block<TIn>(ws, m, in, (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, TMA-fed variant of the kernel above -- the default whenever the logits rows of an
+// utterance are contiguous (unit column stride, which is what the [T, V+2] head-output views are).
+// A CTA owns a contiguous range of 64-frame row blocks and streams them through two shared-memory
+// stages: while block i is normalised and gathered, the TMA engine already copies block i+1 (one
+// 1-D bulk copy of 64 x row_stride elements, mbarrier-signalled; SASS UBLKCP).  No thread ever
+// loads a logit itself, no registers hold loads in flight, and the per-utterance setup (ids,
+// keep-mask, kept list, gather offsets) is reused by the consecutive blocks of one utterance.
+// The copy starts at the 16-byte boundary below the first logit (a view of the head output starts
+// 2 elements in) and is rounded up to 16 bytes; both stay inside the allocation the view lives in.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)
+hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_bytes)
+{
+    constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;                      // rows per warp
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *stage0 = smem_raw;                                        // [2][stage_bytes]
+    int32_t *ids_sm = reinterpret_cast<int32_t *>(smem_raw + 2 * stage_bytes);   // [sp_cap]
+    uint32_t *mask_sm = reinterpret_cast<uint32_t *>(ids_sm + sp_cap);       // [8]
+    int32_t *kept_sm = reinterpret_cast<int32_t *>(mask_sm + 8);             // [256]
+    float2 *stat_sm = reinterpret_cast<float2 *>(kept_sm + 256);             // [64] {max, lse}
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stat_sm + HFA_EMIS_ROWS);   // [2]
+    int32_t *shift_sm = reinterpret_cast<int32_t *>(bar + 2);                // [2] byte shift of a stage
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk0 = (int)(((int64_t)blockIdx.x * n_blocks) / gridDim.x);
+    const int blk1 = (int)(((int64_t)(blockIdx.x + 1) * n_blocks) / gridDim.x);
+    if (blk0 >= blk1) return;
+
+    // thread 0: start the copy of row block `blk` into stage `s`
+    auto issue = [&](int blk, int s) {
+        const int u = ws.block_utt[blk];
+        const HfaUtt m = ws.utt[u];
+        const HfaInput in = ws.inputs[u];
+        const int t_base = (blk - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+        const int rows = min(HFA_EMIS_ROWS, m.T - t_base);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(in.frame) +
+                                   (int64_t)t_base * in.frame_st * (int64_t)sizeof(TIn);
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        // rows-1 full strides plus the V logits of the last row, from the aligned address
+        const uint32_t bytes =
+            (shift + (uint32_t)(((int64_t)(rows - 1) * in.frame_st + V) * (int64_t)sizeof(TIn)) + 15u) & ~15u;
+        shift_sm[s] = (int32_t)shift;
+        hfa_mbar_expect_tx(&bar[s], bytes);
+        hfa_bulk_load(stage0 + (size_t)s * stage_bytes, src - shift, bytes, &bar[s]);
+    };
+    if (tid == 0) {
+        hfa_mbar_init(&bar[0], 1);
+        hfa_mbar_init(&bar[1], 1);
+        hfa_fence_mbar_init();
+        issue(blk0, 0);
+    }
+    __syncthreads();
+
+    int cur_u = -1;
+    int S = 0, Sp = 4, T = 0, n_kept = 0;
+    uint32_t goff[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    HfaUtt m;
+    HfaInput in;
+    for (int blk = blk0; blk < blk1; ++blk) {
+        const int s = (blk - blk0) & 1;
+        if (tid == 0 && blk + 1 < blk1) issue(blk + 1, s ^ 1);     // stage s^1 was released by the
+                                                                   // barrier that ended block blk-1
+        const int u = ws.block_utt[blk];
+        if (u != cur_u) {
+            // B. per-utterance setup: ids, keep mask, kept list, gather offsets
+            cur_u = u;
+            m = ws.utt[u];
+            in = ws.inputs[u];
+            S = m.S; Sp = m.Sp; T = m.T;
+            const int mask_words = (V + 31) >> 5;
+            if (tid < 8) mask_sm[tid] = (tid == 0) ? 1u : 0u;                // id 0 always kept (:39)
+            __syncthreads();
+            const int32_t *ids = ws.ids + m.seg_off;
+            for (int q = tid; q < Sp; q += blockDim.x) {
+                const int id = (q < S) ? ids[q] : V;
+                ids_sm[q] = id;
+                if (q < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+            }
+            __syncthreads();
+            n_kept = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) n_kept += (w < mask_words) ? __popc(mask_sm[w]) : 0;
+            if (tid < V && ((mask_sm[tid >> 5] >> (tid & 31)) & 1u)) {
+                int pos = __popc(mask_sm[tid >> 5] & ((1u << (tid & 31)) - 1u));
+                for (int w = 0; w < (tid >> 5); ++w) pos += __popc(mask_sm[w]);
+                kept_sm[pos] = tid;
+            }
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int s4 = min(lane * 4 + 128 * it, Sp - 4);
+                const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+                goff[it][0] = (uint32_t)id4.x; goff[it][1] = (uint32_t)id4.y;
+                goff[it][2] = (uint32_t)id4.z; goff[it][3] = (uint32_t)id4.w;
+            }
+            __syncthreads();
+        }
+        const int t_base = (blk - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+        const int row_st = (int)in.frame_st;
+
+        hfa_mbar_wait(&bar[s], (uint32_t)(((blk - blk0) >> 1) & 1));
+        const TIn *xs = reinterpret_cast<const TIn *>(stage0 + (size_t)s * stage_bytes + shift_sm[s]);
+
+        // C. normaliser, warp-local: lane -> (row = 8 * warp + lane / 4, part = lane % 4), kept ids
+        //    only.  A warp normalises exactly the 8 consecutive rows it gathers below, so C -> D needs
+        //    no CTA barrier (consecutive rows: their shared-memory banks differ).
+        {
+            const int rr = RPW * warp + (lane >> 2);
+            const TIn *row = xs + rr * row_st;
+            const int part = lane & 3;
+            float mx = HFA_NEG_INF;
+            for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, hfa_to_float<TIn>(row[kept_sm[k]]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.0f;
+            for (int k = part; k < n_kept; k += 4)
+                sum = __fadd_rn(sum, expf(__fsub_rn(hfa_to_float<TIn>(row[kept_sm[k]]), mx)));
+            sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+            sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+            if (part == 0) stat_sm[rr] = make_float2(mx, logf(sum));
+        }
+        __syncwarp();
+
+        // D. gather by phoneme id and store (pad columns: id V -> -inf)
+        {
+            const int rows_here = max(0, min(RPW, T - t_base - RPW * warp));
+            float *dst = ws.emis + m.emis_off + (int64_t)(t_base + RPW * warp) * Sp + lane * 4;
+            const int dst_step = Sp;
+            const bool st0 = lane * 4 < Sp, st1 = lane * 4 + 128 < Sp;
+            auto val = [&](const TIn *row, uint32_t id, const float2 st) {
+                const float x = (id < (uint32_t)V) ? hfa_to_float<TIn>(row[id]) : HFA_NEG_INF;
+                return __fsub_rn(__fsub_rn(x, st.x), st.y);
+            };
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                if (r >= rows_here) break;                                   // warp-uniform
+                const int rr = RPW * warp + r;
+                const float2 st = stat_sm[rr];
+                const TIn *row = xs + rr * row_st;
+                float4 o;
+                o.x = val(row, goff[0][0], st); o.y = val(row, goff[0][1], st);
+                o.z = val(row, goff[0][2], st); o.w = val(row, goff[0][3], st);
+                if (st0) *reinterpret_cast<float4 *>(dst + r * dst_step) = o;
+                if (Sp > 128) {                                              // warp-uniform
+                    o.x = val(row, goff[1][0], st); o.y = val(row, goff[1][1], st);
+                    o.z = val(row, goff[1][2], st); o.w = val(row, goff[1][3], st);
+                    if (st1) *reinterpret_cast<float4 *>(dst + r * dst_step + 128) = o;
+                }
+            }
+            if (Sp > 256) {                                                  // long phoneme sequences
+                for (int r = 0; r < rows_here; ++r) {
+                    const int rr = RPW * warp + r;
+                    const float2 st = stat_sm[rr];
+                    const TIn *row = xs + rr * row_st;
+                    for (int s4 = lane * 4 + 256; s4 < Sp; s4 += 128) {
+                        const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
+                        float4 o;
+                        o.x = val(row, (uint32_t)id4.x, st); o.y = val(row, (uint32_t)id4.y, st);
+                        o.z = val(row, (uint32_t)id4.z, st); o.w = val(row, (uint32_t)id4.w, st);
+                        *reinterpret_cast<float4 *>(dst + r * dst_step + (s4 - lane * 4)) = o;
+                    }
+                }
+            }
+        }
+        __syncthreads();                           // everyone is done with stage s and stat_sm
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Wide vocabularies (V > HFA_EMIS_BLOCK_MAX_V): one warp per row, rows streamed through a per-warp
 // shared-memory buffer, full masked softmax exactly as the reference spells it.
@@ -316,10 +498,30 @@ hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
 }  // namespace
 
 template <typename TIn>
-static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_sp)
+static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_sp, int64_t max_row_stride,
+                                     int *n_launched)
 {
+    *n_launched = 1;
     const int V = c.vocab;
     cudaError_t e;
+    // max_row_stride > 0: every utterance has unit column stride and rows at most that many elements
+    // apart -> a 64-row block is one contiguous range and can travel by TMA
+    const int64_t stage = max_row_stride > 0
+        ? ((HFA_EMIS_ROWS * max_row_stride * (int64_t)sizeof(TIn) + 32 + 127) & ~(int64_t)127) : 0;
+    if (V <= HFA_EMIS_BLOCK_MAX_V && stage > 0 && stage <= 48 * 1024) {
+        const size_t smem = 2 * (size_t)stage + (size_t)max_sp * 4 + 8 * 4 + 256 * 4 + HFA_EMIS_ROWS * 8 +
+                            2 * 8 + 2 * 4 + 16;
+        e = cudaFuncSetAttribute(hfa_emission_stream_kernel<TIn>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = (int)((200 * 1024) / smem);
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        const int grid = blocks < 148 * per_sm ? blocks : 148 * per_sm;
+        *n_launched = 2;     // tells the caller to launch hfa_launch_edge as well (on a forked stream)
+        hfa_emission_stream_kernel<TIn><<<grid, HFA_EMIS_WARPS * 32, smem, c.stream>>>(
+            c.ws, blocks, V, max_sp, (int)stage);
+        return cudaGetLastError();
+    }
     if (V <= HFA_EMIS_BLOCK_MAX_V) {
         const int VP = (V + 1) | 1;
         const size_t smem = (size_t)max_sp * 4 + 8 * 4 + 256 * 4 + HFA_EMIS_ROWS * 8 +
@@ -342,13 +544,27 @@ static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_
     return cudaGetLastError();
 }
 
-cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype)
+cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
+                                int64_t max_row_stride, int *n_launched)
+{
+    *n_launched = 0;
+    if (total_row_blocks <= 0) return cudaSuccess;
+    if (dtype == 0) return launch_emission_t<float>(c, total_row_blocks, max_sp, max_row_stride, n_launched);
+    if (dtype == 1) return launch_emission_t<__half>(c, total_row_blocks, max_sp, max_row_stride, n_launched);
+    if (dtype == 2)
+        return launch_emission_t<__nv_bfloat16>(c, total_row_blocks, max_sp, max_row_stride, n_launched);
+    return cudaErrorInvalidValue;
+}
+
+// the edge stream as its own launch (needed when hfa_launch_emission reported 2 launches)
+cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype)
 {
     if (total_row_blocks <= 0) return cudaSuccess;
-    if (dtype == 0) return launch_emission_t<float>(c, total_row_blocks, max_sp);
-    if (dtype == 1) return launch_emission_t<__half>(c, total_row_blocks, max_sp);
-    if (dtype == 2) return launch_emission_t<__nv_bfloat16>(c, total_row_blocks, max_sp);
-    return cudaErrorInvalidValue;
+    if (dtype == 0) hfa_edge_kernel<float><<<total_row_blocks, HFA_EMIS_ROWS, 0, c.stream>>>(c.ws);
+    else if (dtype == 1) hfa_edge_kernel<__half><<<total_row_blocks, HFA_EMIS_ROWS, 0, c.stream>>>(c.ws);
+    else if (dtype == 2) hfa_edge_kernel<__nv_bfloat16><<<total_row_blocks, HFA_EMIS_ROWS, 0, c.stream>>>(c.ws);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const float *prob_log,
