@@ -163,19 +163,32 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     };
     // flags: 1 = the path moved into this frame's state, 2 = that state is an id-0 (SP) state,
     //        4 = frame past T (no-op), 8 = frame 0 (seed, :250-254)
+    // Raw operands of one frame: nothing here touches a loaded value, so the loads stay in flight
+    // until `finish` turns them into the staged tuple two rounds later.
+    struct Raw { float x, y; float2 ed; int id, st, sprev; };
     auto gather = [&](int round, int st, int sprev) {
+        const int t = min(round * 32 + lane, T - 1);         // clamped: always a valid address
+        const float *row = emis + (int64_t)t * Sp;
+        Raw g;
+        g.x = row[st];
+        g.y = row[sprev];
+        g.ed = edge2[t];
+        g.id = ids[st];
+        g.st = st;
+        g.sprev = sprev;
+        return g;
+    };
+    auto finish = [&](int round, const Raw &g) {
         const int t = round * 32 + lane;
         float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(4));
-        if (round < n_rounds && t < T) {
-            const float *row = emis + (int64_t)t * Sp;
-            const bool moved = (t > 0) && (sprev != st);
-            const float2 ed = edge2[t];
-            v.x = row[st];
-            v.y = moved ? row[sprev] : v.x;
-            v.z = moved ? ed.x : ed.y;
-            int fl = (moved ? 1 : 0) | ((ids[st] == 0) ? 2 : 0);
+        if (t < T) {
+            const bool moved = (t > 0) && (g.sprev != g.st);
+            v.x = g.x;
+            v.y = g.y;
+            v.z = moved ? g.ed.x : g.ed.y;
+            int fl = (moved ? 1 : 0) | ((g.id == 0) ? 2 : 0);
             if (t == 0) {
-                const bool seeded = (st == 0) || (st == 1 && lead_sp);
+                const bool seeded = (g.st == 0) || (g.st == 1 && lead_sp);
                 v.x = seeded ? v.x : HFA_NEG_INF;
                 fl = 8;
             }
@@ -183,16 +196,24 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         }
         return v;
     };
-    int st_cur = load_state(0);
-    int st_nxt = load_state(1);
-    float4 v_cur = gather(0, st_cur, __shfl_up_sync(0xffffffffu, st_cur, 1));
+    // software pipeline: path states three rounds ahead, gathered operands two rounds ahead
+    int st_a = load_state(0), st_b = load_state(1), st_c = load_state(2);
+    Raw g_cur = gather(0, st_a, __shfl_up_sync(0xffffffffu, st_a, 1));
+    Raw g_nxt;
+    {
+        int sp1 = __shfl_up_sync(0xffffffffu, st_b, 1);
+        const int last0 = __shfl_sync(0xffffffffu, st_a, 31);
+        if (lane == 0) sp1 = last0;
+        g_nxt = gather(1, st_b, sp1);
+    }
     for (int r = 0; r < n_rounds; ++r) {
         // issue the loads of the following rounds before touching this round's results
-        const int st_nn = load_state(r + 2);
-        int sprev_n = __shfl_up_sync(0xffffffffu, st_nxt, 1);
-        const int last_cur = __shfl_sync(0xffffffffu, st_cur, 31);
-        if (lane == 0) sprev_n = last_cur;
-        const float4 v_nxt = gather(r + 1, st_nxt, sprev_n);
+        const int st_d = load_state(r + 3);
+        int sp2 = __shfl_up_sync(0xffffffffu, st_c, 1);
+        const int last1 = __shfl_sync(0xffffffffu, st_b, 31);
+        if (lane == 0) sp2 = last1;
+        const Raw g_nn = gather(r + 2, st_c, sp2);
+        const float4 v_cur = finish(r, g_cur);
 
         stage[lane] = v_cur;
         // frames that are not a plain "stay" (moved / seed / past T): one bit per frame, uniform
@@ -253,9 +274,10 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         }
         carry_d = d;
         __syncwarp();
-        st_cur = st_nxt;
-        st_nxt = st_nn;
-        v_cur = v_nxt;
+        st_b = st_c;
+        st_c = st_d;
+        g_cur = g_nxt;
+        g_nxt = g_nn;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) log_sum += __shfl_xor_sync(0xffffffffu, log_sum, o);
