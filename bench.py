@@ -242,9 +242,14 @@ def main():
         torch.cuda.synchronize()
         dt = _lib.DTYPE_F32
 
+        d2h_stream = torch.cuda.Stream()
+        d2h_done = [None] * n_sets
+
         def step(i, evs=None):
             k = i % n_sets
             ws, res = wss[k], ress[k]
+            if d2h_done[k] is not None:          # the last download out of this result buffer
+                torch.cuda.current_stream().wait_event(d2h_done[k])
             if evs is not None:
                 evs[0].record()
             ops.emission(ws, plan.handle, dt)
@@ -256,7 +261,15 @@ def main():
             ops.backtrace(ws, plan.handle, res, None, None)
             if evs is not None:
                 evs[3].record()
-            host_res[k].copy_(res, non_blocking=True)
+            # results go to pinned host memory on their own stream: the download of step i overlaps
+            # the kernels of step i+1 (every step's results still land on the host inside the region)
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ready)
+                host_res[k].copy_(res, non_blocking=True)
+                d2h_done[k] = torch.cuda.Event()
+                d2h_done[k].record()
 
         for i in range(warmup):
             step(i)
@@ -272,6 +285,7 @@ def main():
         e0.record()
         for i in range(steps):
             step(i, stage_evs[i])
+        torch.cuda.current_stream().wait_stream(d2h_stream)      # the last download is inside the region
         e1.record()
         torch.cuda.synchronize()
         clk = clocks.stop()
