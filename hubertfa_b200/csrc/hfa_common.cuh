@@ -104,6 +104,24 @@ __device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool hfa_mbar_test_wait(uint64_t *bar, uint32_t parity)   // non-blocking
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(hfa_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void hfa_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hfa_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void hfa_mbar_wait(uint64_t *bar, uint32_t parity)
 {
     // try_wait suspends the thread for a hardware time slice; a copy that never lands (a bug) must
