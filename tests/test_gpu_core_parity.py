@@ -64,6 +64,18 @@ def test_random_shapes_all_classes(routing):
             raise AssertionError(f"shape {shp}: {e}") from e
 
 
+def test_wavefront_cta_kernel(monkeypatch):
+    """HFA_CTA_WAVE=1: the flag-synchronised (barrier-free) variant of the CTA-per-utterance kernel."""
+    monkeypatch.setenv("HFA_CTA_WAVE", "1")
+    shapes = [(600, 257, "alternate"), (700, 300, "alternate"), (1000, 513, "alternate"),
+              (1300, 1030, "alternate"), (50, 2100, "dictionary"), (1, 300, "alternate")]
+    ins = [synth_core_inputs(T, S, 63, 7000 + i, style, planted=bool(i % 2)) for i, (T, S, style) in enumerate(shapes)]
+    out = run_core_gpu([x["ids"] for x in ins], [x["prob_log"] for x in ins], [x["el"] for x in ins],
+                       [x["ne"] for x in ins], [x["p"] for x in ins], 0.02)
+    for x, g in zip(ins, out):
+        check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], g, x["p"], 0.02)
+
+
 def test_ties_go_to_the_earlier_candidate(routing):
     """Constant emissions and edge logs make stay/advance/skip tie everywhere: the strict '>' scan
     (alignment_decoder.py:210-218) must be reproduced exactly."""
