@@ -89,8 +89,13 @@ class HostBatchAligner:
     what bounds the pipeline depth.
     """
 
+    # byte shares of the chunks, first to last: the early chunks are big (their alignment overlaps the
+    # rest of the upload anyway), the last one is small so that little is left when the upload ends
+    DEFAULT_SHARES = (0.30, 0.28, 0.22, 0.12, 0.08)
+
     def __init__(self, T, S, ph_ids, vocab_size, frame_length, row_width, frame_col=2, edge_col=0,
-                 n_chunks=4, device=None, dtype=torch.float32, pool: "BufferPool | None" = None):
+                 n_chunks=None, device=None, dtype=torch.float32, pool: "BufferPool | None" = None,
+                 shares=None):
         self.lib = _lib.load()
         self.T = np.ascontiguousarray(T, dtype=np.int32)
         self.S = np.ascontiguousarray(S, dtype=np.int32)
@@ -100,33 +105,41 @@ class HostBatchAligner:
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
         self.dt = ops.TORCH_TO_DTYPE[dtype]
-        self.row_width = W = int(row_width)
-        self.esz = esz = torch.empty(0, dtype=dtype).element_size()
+        self.row_width = int(row_width)
+        self.frame_col, self.edge_col = int(frame_col), int(edge_col)
+        self.esz = torch.empty(0, dtype=dtype).element_size()
+        if shares is None:
+            shares = self.DEFAULT_SHARES if n_chunks is None else [1.0 / max(int(n_chunks), 1)] * max(int(n_chunks), 1)
+        self.shares = np.asarray(shares, dtype=np.float64) / float(np.sum(shares))
+        # only what the upload itself needs is computed here; the per-chunk tables are built in run()
+        # while the first chunks are already on the wire
         self.row_off = np.concatenate([[0], np.cumsum(self.T.astype(np.int64))])
+        cuts = np.searchsorted(self.row_off[1:], self.row_off[-1] * np.cumsum(self.shares)[:-1]) + 1
+        self.bounds = np.unique(np.concatenate([[0], np.minimum(cuts, self.n_utt), [self.n_utt]]))
+        self.chunks = None
+        self.pool = pool if pool is not None else BufferPool(self.dev)
+        self.h2d_bytes = int(self.row_off[-1]) * self.row_width * self.esz
+        self.d2h_bytes = 0
+
+    def _build_chunks(self):
+        W, esz = self.row_width, self.esz
         seg_off = np.concatenate([[0], np.cumsum(np.maximum(self.S, 0).astype(np.int64))])
-        n_chunks = max(1, min(int(n_chunks), max(self.n_utt, 1)))
-        # contiguous utterance ranges of about equal bytes
-        cuts = np.searchsorted(self.row_off[1:], self.row_off[-1] * (np.arange(1, n_chunks) / n_chunks)) + 1
-        bounds = np.unique(np.concatenate([[0], np.minimum(cuts, self.n_utt), [self.n_utt]]))
         self.chunks = []
-        for ci in range(len(bounds) - 1):
+        for ci in range(len(self.bounds) - 1):
             c = _Chunk()
-            c.b0, c.b1 = int(bounds[ci]), int(bounds[ci + 1])
+            c.b0, c.b1 = int(self.bounds[ci]), int(self.bounds[ci + 1])
             c.r0, c.r1 = int(self.row_off[c.b0]), int(self.row_off[c.b1])
             c.T = np.ascontiguousarray(self.T[c.b0:c.b1])
             c.S = np.ascontiguousarray(self.S[c.b0:c.b1])
             c.ids = np.ascontiguousarray(self.ids[seg_off[c.b0]:seg_off[c.b1]])
             c.seg_off = seg_off[c.b0:c.b1 + 1] - seg_off[c.b0]
             rows = self.row_off[c.b0:c.b1] - c.r0
-            c.frame_ptr_off = np.ascontiguousarray((rows * W + int(frame_col)) * esz)
-            c.edge_ptr_off = np.ascontiguousarray((rows * W + int(edge_col)) * esz)
+            c.frame_ptr_off = np.ascontiguousarray((rows * W + self.frame_col) * esz)
+            c.edge_ptr_off = np.ascontiguousarray((rows * W + self.edge_col) * esz)
             c.stride = np.full(c.b1 - c.b0, W, dtype=np.int64)
             c.ones = np.ones(c.b1 - c.b0, dtype=np.int64)
             c.stream = _side_stream(self.dev, 1 + ci)
             self.chunks.append(c)
-        self.pool = pool if pool is not None else BufferPool(self.dev)
-        self.h2d_bytes = int(self.row_off[-1]) * W * esz
-        self.d2h_bytes = 0
 
     def run(self, head_host: torch.Tensor, profile: bool = False) -> dict:
         """head_host: pinned host tensor [sum T, row_width].  Returns per-utterance arrays
@@ -150,12 +163,15 @@ class HostBatchAligner:
             # 1. every chunk goes on the wire, in order, before any host-side collation
             staged = []
             with torch.cuda.stream(copy_stream):
-                for c in self.chunks:
-                    dev_head = pool.device_bytes(max(c.r1 - c.r0, 1) * W * esz).view(self.dtype).view(-1, W)
-                    dev_head[: c.r1 - c.r0].copy_(head_host[c.r0:c.r1], non_blocking=True)
+                for ci in range(len(self.bounds) - 1):
+                    r0, r1 = int(self.row_off[self.bounds[ci]]), int(self.row_off[self.bounds[ci + 1]])
+                    dev_head = pool.device_bytes(max(r1 - r0, 1) * W * esz).view(self.dtype).view(-1, W)
+                    dev_head[: r1 - r0].copy_(head_host[r0:r1], non_blocking=True)
                     landed = torch.cuda.Event(enable_timing=profile)
                     landed.record(copy_stream)
                     staged.append((dev_head, landed))
+            if self.chunks is None:
+                self._build_chunks()
             # 2. collation + launches of chunk i while the later chunks are still travelling
             prof = []
             for c, (dev_head, landed) in zip(self.chunks, staged):

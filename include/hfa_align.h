@@ -100,6 +100,9 @@ int hfa_plan_upload(const hfa_plan *plan, void *workspace /*[dev]*/, void *strea
 /* hfa_set_inputs: frame_ptrs[b] -> logits of utterance b addressed as
  * base[t*frame_stride_t[b] + v*frame_stride_v[b]] (elements; the reference receives strided views of
  * the [1,T,V+2] head output, networks/task/forced_alignment.py:288-291); edge_ptrs[b][t*edge_stride[b]].
+ * When every utterance has unit column stride the rows travel by TMA in 16-byte units: the logits
+ * must then be readable from the 16-byte boundary below a block's first logit to the one above its
+ * last (always true for views of a larger tensor and for allocator-aligned buffers).
  * The tables are [host] arrays of [dev] pointers; this call copies them into the workspace (a
  * pageable-memory H2D copy, so it is NOT capturable into a CUDA graph; every other compute entry
  * point only launches kernels and is). */

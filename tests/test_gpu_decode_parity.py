@@ -86,6 +86,36 @@ def test_emission_kernel_vs_oracle_and_torch(dtype, V):
         fo += (T + 15) // 16 * 16
 
 
+def test_emission_fallback_for_non_unit_column_stride():
+    """Logits stored [V, T] (a transposed view: column stride != 1) cannot travel by TMA and take the
+    thread-loaded block kernel; results must equal the TMA path on the same values."""
+    dev = torch.device("cuda")
+    V = 63
+    shapes = [(200, 30), (65, 150), (64, 7)]
+    ids_list, fr_t, fr_c, edges = [], [], [], []
+    for i, (T, S) in enumerate(shapes):
+        rng = np.random.default_rng(700 + i)
+        vocab = synth.make_vocab(V)
+        ph_seq, _, _ = synth.make_ph_seq(rng, S, V, "dictionary")
+        ids_list.append(np.array([vocab["vocab"][p] for p in ph_seq], dtype=np.int32))
+        g = torch.Generator().manual_seed(700 + i)
+        x = (3.0 * torch.randn(V, T, generator=g)).to(dev)
+        fr_t.append(x.t())                         # [T, V] view with strides (1, T)
+        fr_c.append(x.t().contiguous())            # same values, unit column stride
+        edges.append((2.0 * torch.randn(T, generator=g)).to(dev))
+    outs = []
+    for frames in (fr_t, fr_c):
+        plan, ws = _emission_gpu(frames, edges, ids_list, V)
+        outs.append((_ws_region(plan, ws, "emis").cpu().numpy().copy(),
+                     _ws_region(plan, ws, "edge2").cpu().numpy().copy()))
+    # same kept-id summation order in both kernels -> identical bits
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    fo = 0
+    for (T, S) in shapes:
+        assert np.array_equal(outs[0][1][fo:fo + T].view(np.uint32), outs[1][1][fo:fo + T].view(np.uint32))
+        fo += (T + 15) // 16 * 16
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_decode_matches_reference_golden(golden, name):
     c = golden.case(name)

@@ -17,7 +17,7 @@ def tm(f, n=20):
     for _ in range(n): f()
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e3
-for ch in (1, 2, 4, 8):
+for ch in (None, 1, 4, 8):
     al = HostBatchAligner(T, S, ids, V, 0.02, V + 2, n_chunks=ch, device=dev, pool=pool)
     print(f"chunks={ch}: run {tm(lambda: al.run(head)):.3f} ms")
     torch.cuda.synchronize()
