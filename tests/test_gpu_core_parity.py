@@ -127,3 +127,36 @@ def test_long_form_c3_stress():
     out = run_core_gpu([x["ids"]], [x["prob_log"]], [x["el"]], [x["ne"]], [x["p"]], dump=False)
     r = check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], out[0], x["p"], full=False)
     assert len(r["ph_idx_seq"]) > 1000
+
+
+def test_many_small_tie_heavy_utterances(routing):
+    """300 small utterances in one batch: random SP patterns, coarse-grid values (ties everywhere),
+    constant emissions, sprinkled -inf, T < S -- every dp cell, backpointer and path vs the C oracle."""
+    from oracle import hfa_oracle_np as onp
+    rng = np.random.default_rng(20241018)
+    ids_l, e_l, el_l, ne_l, p_l = [], [], [], [], []
+    for i in range(300):
+        T, S = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        sp_rate = [0.0, 0.3, 0.5, 0.8, 1.0][i % 5]
+        ids = np.where(rng.random(S) < sp_rate, 0, rng.integers(1, 30, S)).astype(np.int32)
+        mode = i % 3
+        if mode == 0:
+            e = (-rng.exponential(3.0, (T, S))).astype(np.float32)
+            p = rng.random(T).astype(np.float32)
+        elif mode == 1:
+            e = (-rng.integers(0, 4, (T, S)) * 0.5).astype(np.float32)
+            p = (rng.integers(0, 3, T) * 0.5).astype(np.float32)
+        else:
+            e = np.full((T, S), -1.0, np.float32)
+            p = np.full(T, 0.25, np.float32)
+        if i % 4 == 0:
+            e[rng.random((T, S)) < 0.05] = -np.inf
+        _, ep = onp.edge_streams(p)
+        el, ne = onp.edge_logs(ep)
+        ids_l.append(ids); e_l.append(e); el_l.append(el); ne_l.append(ne); p_l.append(p)
+    out = run_core_gpu(ids_l, e_l, el_l, ne_l, p_l, 0.0116)
+    for i, g in enumerate(out):
+        try:
+            check_core_against_oracle(ids_l[i], e_l[i], el_l[i], ne_l[i], g, p_l[i], 0.0116)
+        except AssertionError as err:
+            raise AssertionError(f"utterance {i} (T={e_l[i].shape[0]}, S={len(ids_l[i])}): {err}") from err
