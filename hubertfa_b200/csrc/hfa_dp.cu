@@ -508,12 +508,12 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
 // ---------------------------------------------------------------------------------------------
 constexpr int HFA_WAVE_RING = 64;
 
-template <int NT>
+template <int K, int NT>
 __global__ void __launch_bounds__(NT)
 hfa_dp_wave_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int stage_floats,
                    float *__restrict__ dp_dump)
 {
-    constexpr int K = HFA_CTA_K, NST = HFA_CTA_STAGES;
+    constexpr int NST = HFA_CTA_STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [stages x stage_floats f32][one slack row][stages x 16 float2][full, empty mbarriers]
     // [32 x 64 float2 ring][32 flags]
@@ -770,7 +770,8 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
     if (e != cudaSuccess) return e;                                                                \
     hfa_dp_cta_kernel<KK, NT><<<n, threads, smem, c.stream>>>(c.ws, order, tile_t, stage_floats,   \
                                                              dp_dump)
-    if (k == 2) {
+    const char *lat_env = getenv("HFA_LATENCY_KERNEL");
+    if (k == 2 && lat_env && lat_env[0] == 'b') {       // barrier variant of the latency routing
         if (threads > 128) return cudaErrorInvalidValue;
         HFA_CTA_LAUNCH(2, 128);
         return cudaGetLastError();
@@ -779,7 +780,7 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
     // B200 both take ~1100 cycles per frame for S = 2000 (16.9 vs 17.8 ms on config 3): the frame
     // time is the instruction stream of 2000 states on ONE SM, not the synchronisation.
     const char *wave_env = getenv("HFA_CTA_WAVE");
-    if (!(wave_env && wave_env[0] == '1')) {
+    if (k != 2 && !(wave_env && wave_env[0] == '1')) {
         if (threads <= 256) { HFA_CTA_LAUNCH(HFA_CTA_K, 256); }
         else if (threads <= 512) { HFA_CTA_LAUNCH(HFA_CTA_K, 512); }
         else { HFA_CTA_LAUNCH(HFA_CTA_K, 1024); }
@@ -790,14 +791,18 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
     const size_t wsmem = ((size_t)HFA_CTA_STAGES * stage_floats + max_sp) * sizeof(float) +
                          HFA_CTA_STAGES * HFA_TILE_T * sizeof(float2) + 2 * HFA_CTA_STAGES * sizeof(uint64_t) +
                          32 * HFA_WAVE_RING * sizeof(float2) + 32 * sizeof(int);
-#define HFA_WAVE_LAUNCH(NT)                                                                        \
-    e = cudaFuncSetAttribute(hfa_dp_wave_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)wsmem);                                                          \
+#define HFA_WAVE_LAUNCH(KK, NT)                                                                    \
+    e = cudaFuncSetAttribute(hfa_dp_wave_kernel<KK, NT>,                                           \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);             \
     if (e != cudaSuccess) return e;                                                                \
-    hfa_dp_wave_kernel<NT><<<n, threads, wsmem, c.stream>>>(c.ws, order, tile_t, stage_floats, dp_dump)
-    if (threads <= 256) { HFA_WAVE_LAUNCH(256); }
-    else if (threads <= 512) { HFA_WAVE_LAUNCH(512); }
-    else { HFA_WAVE_LAUNCH(1024); }
+    hfa_dp_wave_kernel<KK, NT><<<n, threads, wsmem, c.stream>>>(c.ws, order, tile_t, stage_floats, \
+                                                               dp_dump)
+    if (k == 2) {
+        if (threads > 128) return cudaErrorInvalidValue;
+        HFA_WAVE_LAUNCH(2, 128);
+    } else if (threads <= 256) { HFA_WAVE_LAUNCH(HFA_CTA_K, 256); }
+    else if (threads <= 512) { HFA_WAVE_LAUNCH(HFA_CTA_K, 512); }
+    else { HFA_WAVE_LAUNCH(HFA_CTA_K, 1024); }
 #undef HFA_WAVE_LAUNCH
     return cudaGetLastError();
 }

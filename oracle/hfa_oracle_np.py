@@ -282,3 +282,49 @@ def ctc_greedy(ctc_logits_np: np.ndarray) -> np.ndarray:
     lab = np.argmax(ctc_logits_np, axis=-1)
     prev = np.concatenate([[0], lab[:-1]])
     return lab[(lab != prev) & (lab != 0)]
+
+
+# --------------------------------------------------------------------------------------------
+# gap post-processing (tools/post_processing.py, cited as pp:<line>)
+# --------------------------------------------------------------------------------------------
+def fill_small_gaps_loop(seq, intervals, wav_length, min_sp=0.1, merge=0.3):
+    """pp:31-65 restated as a plain loop over gaps; returns a new f64 [n,2] array."""
+    iv = np.array(intervals, dtype=F64, copy=True)
+    n = len(seq)
+    if 0 < iv[0, 0] < min_sp:                                   # pp:32-34
+        iv[0, 0] = 0
+    for i in range(n - 1):                                      # pp:36-59
+        a, b = iv[i, 1], iv[i + 1, 0]
+        if not (a < b and b - a < merge):
+            continue
+        left_ap, right_ap = seq[i] == "AP", seq[i + 1] == "AP"
+        if left_ap and not right_ap:
+            iv[i, 1] = b
+        elif right_ap and not left_ap:
+            iv[i + 1, 0] = a
+        elif (left_ap and right_ap) or b - a < min_sp:
+            iv[i, 1] = iv[i + 1, 0] = (a + b) / 2
+    if iv[-1, 1] < wav_length and wav_length - iv[-1, 1] < min_sp:   # pp:61-63
+        iv[-1, 1] = wav_length
+    return iv
+
+
+def add_sp_loop(seq, intervals, wav_length, add_phone="SP"):
+    """pp:5-28 restated: silence in front (unless the first interval starts at <= 0), in every gap,
+    and at the end.  Returns (labels, f64 [m,2])."""
+    if len(seq) == 0:
+        return [add_phone], np.array([[0.0, wav_length]], dtype=F64)
+    iv = np.asarray(intervals, dtype=F64)
+    labels, rows = [], []
+    cursor = 0.0
+    for k, (w, (s, e)) in enumerate(zip(seq, iv)):
+        if (k == 0 and s > 0) or (k > 0 and cursor < s):
+            labels.append(add_phone)
+            rows.append([cursor, s])
+        labels.append(w)
+        rows.append([s, e])
+        cursor = e
+    if cursor < wav_length:
+        labels.append(add_phone)
+        rows.append([cursor, wav_length])
+    return labels, np.array(rows, dtype=F64)
