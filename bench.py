@@ -213,6 +213,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hubertfa_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    try:        # pin this rank to the CPUs next to its GPU (matters for the host-driven e2e leg at N > 1)
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only

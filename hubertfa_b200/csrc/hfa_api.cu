@@ -21,6 +21,8 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
                                    float *dp_dump);
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
+cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
+                               float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
                                 int64_t max_row_stride, int *n_launched);
 cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype);
@@ -96,6 +98,11 @@ struct hfa_plan {
     int32_t cta_max_sp = 0, max_sp = 4;
     int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
     int32_t lat_begin = 0, lat_count = 0, lat_max_sp = 0;            // small-batch latency routing
+    // banded (halo) kernel work lists: [0] S <= 256 utterances of a small batch (latency regime,
+    // 2 states per lane), [1] long phoneme sequences (S > 256, band_k[1] states per lane)
+    std::vector<HfaBandItem> band_items;
+    int32_t band_begin[2] = {0, 0}, band_count[2] = {0, 0}, band_k[2] = {2, 4};
+    int64_t band_xchg_elems = 0;
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
     std::vector<int32_t> block_utt;            // [row_blocks[n]]
@@ -104,7 +111,7 @@ struct hfa_plan {
     // byte offsets
     int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
-            o_last = 0, ws_bytes = 0;
+            o_last = 0, o_band_items = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
     std::vector<unsigned char> head;           // host image of the head (without inputs)
     // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
     // aligned base pointers and positive row strides of at most this many elements (TMA path)
@@ -132,6 +139,9 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.rev_idx = reinterpret_cast<int32_t *>(b + p->o_revi);
     w.rev_t = reinterpret_cast<int32_t *>(b + p->o_revt);
     w.dp_last = reinterpret_cast<float *>(b + p->o_last);
+    w.band_items = reinterpret_cast<const HfaBandItem *>(b + p->o_band_items);
+    w.band_ticket = reinterpret_cast<int32_t *>(b + p->o_band_ticket);
+    w.band_xchg = reinterpret_cast<uint4 *>(b + p->o_band_xchg);
     return w;
 }
 
@@ -255,15 +265,24 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             p->order.insert(p->order.end(), lists[c].begin(), lists[c].end());
             all.insert(all.end(), lists[c].begin(), lists[c].end());
         }
-        // Experimental routing (HFA_LATENCY_MODE=1, off by default): utterances with more than 2
-        // states per lane go to the multi-warp kernel (2 states per thread, ceil(Sp/64) warps).
-        // Measured on B200 (config 2) the per-frame barrier costs more than the shorter per-warp
-        // instruction stream saves (0.317 ms vs 0.271 ms for the DP stage), so it stays opt-in; the
-        // parity tests run both routings.
-        bool latency = false;
-        if (const char *e = std::getenv("HFA_LATENCY_MODE")) latency = (e[0] == '1');
-        std::vector<int32_t> lat;
-        if (latency) {
+        // Routing.  The recurrence is a serial chain in t, so a batch that cannot fill the machine
+        // with one warp per utterance (BASELINE configs 1-3) is bounded by the per-frame latency of
+        // its longest utterances.  Such batches go to the banded kernel (hfa_dp_band_kernel): every
+        // utterance becomes several 2-states-per-lane warps on different SMs.  Big batches keep
+        // one warp per utterance (no redundant halo work).
+        //   HFA_LATENCY_MODE = 0: never band (S <= 256) | 2: always band | 1: the older multi-warp
+        //   CTA kernel with a barrier per frame | unset: band when the batch has <= HFA_BAND_MAX
+        //   (default 1184 = 8 per SM) band warps.   HFA_BIG_KERNEL = cta | band, HFA_BIG_K = 2|4|8.
+        auto n_bands = [&](int32_t b, int k) {
+            const int w = 32 * k, own = w - 32, sp = p->utt[b].Sp;
+            return sp <= w ? 1 : (sp - 32 + own - 1) / own;
+        };
+        int64_t band_max = 1184;
+        if (const char *e = std::getenv("HFA_BAND_MAX")) band_max = std::atoll(e);
+        int lat_mode = -1;
+        if (const char *e = std::getenv("HFA_LATENCY_MODE")) lat_mode = e[0] - '0';
+        std::vector<int32_t> lat, lat_band;
+        if (lat_mode == 1) {
             for (int c = 2; c < HFA_NUM_CLASSES; ++c) {
                 lat.insert(lat.end(), lists[c].begin(), lists[c].end());
                 for (int32_t b : lists[c]) p->lat_max_sp = std::max(p->lat_max_sp, p->utt[b].Sp);
@@ -271,7 +290,55 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 p->class_count[c] = 0;
             }
             std::sort(lat.begin(), lat.end(), by_len);
+        } else if (lat_mode != 0) {
+            int64_t nb = 0;
+            bool any_split = false;
+            for (int c = 0; c < HFA_NUM_CLASSES; ++c)
+                for (int32_t b : lists[c]) {
+                    nb += n_bands(b, 2);
+                    any_split = any_split || c >= 2;
+                }
+            if (lat_mode == 2 || (any_split && nb <= band_max)) {
+                for (int c = 0; c < HFA_NUM_CLASSES; ++c) {
+                    lat_band.insert(lat_band.end(), lists[c].begin(), lists[c].end());
+                    lists[c].clear();
+                    p->class_count[c] = 0;
+                }
+                std::sort(lat_band.begin(), lat_band.end(), by_len);
+            }
         }
+        std::vector<int32_t> big_band;
+        {
+            int big_k = 4;
+            if (const char *e = std::getenv("HFA_BIG_K")) big_k = std::atoi(e);
+            if (big_k != 2 && big_k != 4 && big_k != 8) big_k = 4;
+            p->band_k[1] = big_k;
+            int big_mode = -1;                               // -1 auto, 0 cta, 1 band
+            if (const char *e = std::getenv("HFA_BIG_KERNEL")) big_mode = (e[0] == 'b');
+            int64_t nb = 0;
+            for (int32_t b : lists[HFA_NUM_CLASSES]) nb += n_bands(b, big_k);
+            if (big_mode == 1 || (big_mode == -1 && nb <= band_max)) {
+                big_band = lists[HFA_NUM_CLASSES];
+                lists[HFA_NUM_CLASSES].clear();
+                p->class_count[HFA_NUM_CLASSES] = 0;
+            }
+        }
+        auto add_bands = [&](const std::vector<int32_t> &utts, int which) {
+            const int k = p->band_k[which];
+            p->band_begin[which] = (int32_t)p->band_items.size();
+            for (int32_t b : utts) {
+                const int nb = n_bands(b, k);
+                const int64_t tiles = (p->utt[b].T + 15) / 16;
+                for (int j = 0; j < nb; ++j) {
+                    const bool has_right = j + 1 < nb;
+                    p->band_items.push_back(HfaBandItem{b, j, has_right ? p->band_xchg_elems : 0});
+                    if (has_right) p->band_xchg_elems += tiles * 32;
+                }
+            }
+            p->band_count[which] = (int32_t)p->band_items.size() - p->band_begin[which];
+        };
+        add_bands(lat_band, 0);
+        add_bands(big_band, 1);
         // merged warp-kernel list: longest expected run time first (frames x per-frame cost, which
         // grows with the states per lane)
         std::vector<int32_t> warp_all;
@@ -304,6 +371,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         for (int32_t b = 0; b < n_utt; ++b)
             p->block_utt.insert(p->block_utt.end(), (size_t)(p->row_blocks[b + 1] - p->row_blocks[b]), b);
         p->o_blkutt = region((int64_t)p->block_utt.size() * 4);
+        p->o_band_items = region((int64_t)p->band_items.size() * sizeof(HfaBandItem));
         p->head_bytes = o;
         p->o_inputs = region((int64_t)n_utt * sizeof(HfaInput));
         p->o_emis = region(emis * 4);
@@ -314,6 +382,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_revi = region(p->total_states * 4);
         p->o_revt = region(p->total_states * 4);
         p->o_last = region((int64_t)n_utt * 8);
+        p->o_band_ticket = region(p->band_items.empty() ? 0 : 8);
+        p->o_band_xchg = region(p->band_xchg_elems * 16);
+        p->band_bytes = o - p->o_band_ticket;
         p->ws_bytes = std::max<int64_t>(o, 256);
 
         p->head.assign((size_t)p->head_bytes, 0);
@@ -323,6 +394,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 std::memcpy(p->head.data() + p->o_ids, p->ids.data(), (size_t)p->total_states * 4);
             std::memcpy(p->head.data() + p->o_order, p->order.data(), p->order.size() * 4);
         }
+        if (!p->band_items.empty())
+            std::memcpy(p->head.data() + p->o_band_items, p->band_items.data(),
+                        p->band_items.size() * sizeof(HfaBandItem));
         std::memcpy(p->head.data() + p->o_rowblk, p->row_blocks.data(), (size_t)(n_utt + 1) * 4);
         if (!p->block_utt.empty())
             std::memcpy(p->head.data() + p->o_blkutt, p->block_utt.data(), p->block_utt.size() * 4);
@@ -402,6 +476,11 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
     cudaError_t e = cudaMemcpyAsync(workspace, p->head.data(), (size_t)p->head_bytes,
                                     cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload");
+    if (p->band_bytes > 0) {       // band tickets + exchange slots start (and are left) all-zero
+        e = cudaMemsetAsync(static_cast<unsigned char *>(workspace) + p->o_band_ticket, 0,
+                            (size_t)p->band_bytes, static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload: band table reset");
+    }
     return HFA_OK;
 }
 
@@ -513,7 +592,7 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
     const int n_cta = p->class_count[HFA_NUM_CLASSES];
     // launches of this call: (merged ? 1 : one per class) + the CTA-per-utterance kernel
     struct Item { int k; const int32_t *order; int n; };
-    Item items[HFA_NUM_CLASSES + 3];
+    Item items[HFA_NUM_CLASSES + 4];
     int n_items = 0;
     if (mode == 0) {
         if (p->warp_all_count > 0)
@@ -523,7 +602,9 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             if (p->class_count[k] > 0)
                 items[n_items++] = {k + 1, c.ws.order + p->class_begin[k], p->class_count[k]};
     }
+    if (p->band_count[0] > 0) items[n_items++] = {-3, nullptr, 0};
     if (p->lat_count > 0) items[n_items++] = {-2, c.ws.order + p->lat_begin, p->lat_count};
+    if (p->band_count[1] > 0) items[n_items++] = {-4, nullptr, 1};
     if (n_cta > 0) items[n_items++] = {-1, c.ws.order + p->class_begin[HFA_NUM_CLASSES], n_cta};
     if (n_items == 0) return HFA_OK;
 
@@ -548,6 +629,12 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             e = hfa_launch_dp_warp_any(c, p->warp_max_k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k > 0)
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
+        else if (items[it].k == -3)
+            e = hfa_launch_dp_band(c, p->band_k[0], p->band_begin[0], p->band_count[0], c.ws.band_ticket,
+                                   dp_dump);
+        else if (items[it].k == -4)
+            e = hfa_launch_dp_band(c, p->band_k[1], p->band_begin[1], p->band_count[1],
+                                   c.ws.band_ticket + 1, dp_dump);
         else if (items[it].k == -2)
             e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else

@@ -38,6 +38,13 @@ struct HfaInput {                // per-utterance logits descriptor (changes per
     int64_t frame_st, frame_sv, edge_st;
 };
 
+// one band of one utterance in the banded (halo) DP kernel: consecutive table entries are
+// consecutive bands of one utterance
+struct HfaBandItem {
+    int32_t utt, band;
+    int64_t xoff;                // uint4 index of this band's exchange slots [n_tiles][32] (0 if unused)
+};
+
 // device-side view of the workspace (pointers computed on the host from the plan's layout)
 struct HfaWs {
     const HfaUtt *utt;
@@ -54,6 +61,10 @@ struct HfaWs {
     int32_t *rev_idx;            // [sum S] segments in backward order
     int32_t *rev_t;              // [sum S]
     float *dp_last;              // end-of-forward scores: [n_utt][2] = dp[T-1][S-1], dp[T-1][S-2]
+    const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
+    int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
+    uint4 *band_xchg;            // {dp, tag, curr, tag} of a band's last 32 states after every tile;
+                                 // all-zero between calls (zeroed by hfa_plan_upload, then by its readers)
 };
 
 #define HFA_NEG_INF __uint_as_float(0xff800000u)

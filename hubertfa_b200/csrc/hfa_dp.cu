@@ -671,6 +671,244 @@ hfa_dp_wave_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Banded (halo) kernel: SEVERAL WARPS PER UTTERANCE ON DIFFERENT SMs, one exchange per 16 frames.
+//
+// State i at frame t only depends on states i, i-1, i-2 at frame t-1 (alignment_decoder.py:177-202),
+// so over a 16-frame tile a state is a function of the 32 states to its left at the start of the
+// tile.  A band is one warp (its own CTA) that holds a window of W = 32 K consecutive states, K per
+// lane; windows of neighbouring bands overlap by 32 states: band b covers [b (W-32), b (W-32) + W).
+// The first 32 states of a window (b > 0) are the HALO: they are recomputed from the left
+// neighbour's values at the start of every tile, go stale from the left edge at two states per
+// frame, and the stale region reaches the first owned state exactly when the tile ends.  After each
+// tile the left band publishes {dp, curr} of its last 32 states (= the halo of its right
+// neighbour) and bumps a flag; neighbours never talk inside a tile, so the bands of one utterance
+// run as a pipeline skewed by 1-2 tiles across SMs instead of a serial chain on one lane set.
+//   * small batches (latency regime): K = 2 -- every utterance with more than 64 states becomes
+//     ceil((Sp-32)/32) warps whose per-frame instruction stream is that of the K = 2 warp kernel;
+//   * long phoneme sequences (S > 256, BASELINE config 3): K = 4 -- 2000 states = 21 warps on 21 SMs
+//     instead of one CTA with a barrier per frame.
+// Work items are claimed through an atomic ticket, so a band's left neighbour has always started
+// before the band itself (no reliance on block dispatch order); band 0 never waits.
+// Extra HBM/L2 traffic: 256 B per band per tile each way (0.5 B per owned cell at K = 2).
+// ---------------------------------------------------------------------------------------------
+// exchange slot of one state: {dp bits, tag, curr bits, tag}, tag = tile + 1.  Each 8-byte half
+// carries its own tag (8-byte accesses are single-copy atomic), so the reader needs no flag and no
+// fence: a half is valid iff its tag matches.  The reader zeroes a slot after use, so the table is
+// all-zero between calls (it is zeroed once by hfa_plan_upload).
+__device__ __forceinline__ uint4 hfa_ld_slot(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void hfa_st_slot(uint4 *p, uint4 v)
+{
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+constexpr int HFA_BAND_STAGES = 3;
+
+template <int K> constexpr size_t hfa_band_smem_bytes()
+{
+    // [stages x 16 rows x 32K floats][slack row][stages x 16 edge pairs][slack pair][mbarriers][ticket]
+    return (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 1) * 32 * K * sizeof(float) +
+           (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 1) * sizeof(float2) +
+           HFA_BAND_STAGES * sizeof(uint64_t) + 16;
+}
+
+template <int K, bool DUMP>
+__global__ void __launch_bounds__(32)
+hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump)
+{
+    static_assert(32 % K == 0 && K >= 2, "the halo (32 states) must be a whole number of lanes");
+    constexpr int TT = HFA_TILE_T, NST = HFA_BAND_STAGES;
+    constexpr int W = 32 * K, OWN = W - 32, HL = 32 / K;     // HL = halo lanes = publishing lanes
+    constexpr int TILE_FLOATS = TT * W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile0 = reinterpret_cast<float *>(smem_raw);
+    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + W);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
+    int *slot = reinterpret_cast<int *>(bar + NST);
+
+    const int lane = threadIdx.x;
+    if (lane == 0) *slot = (int)atomicInc(reinterpret_cast<unsigned int *>(ticket), gridDim.x - 1);
+    __syncwarp();
+    const int item = item_begin + *slot;                       // wraps back to 0 after the last CTA
+    const HfaBandItem bi = ws.band_items[item];
+    const int u = bi.utt, band = bi.band;
+    const HfaUtt m = ws.utt[u];
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int c0 = band * OWN;                                 // first state of the window
+    const int first = c0 + lane * K;                           // first state of this lane
+    const int n_bands = Sp <= W ? 1 : (Sp - 32 + OWN - 1) / OWN;
+    const bool has_left = band > 0, has_right = band + 1 < n_bands;
+    const bool owner = !has_left || lane >= HL;                // lanes whose states this band owns
+    const int n_tiles = (T + TT - 1) / TT;
+    const int cols = min(W, Sp - c0);                          // window columns that exist (% 4 == 0)
+    const float *g_emis = ws.emis + m.emis_off + c0;
+    const float2 *g_edge = ws.edge2 + m.edge_off;
+    uint32_t *g_bp = ws.bp + m.bp_off;
+    const double ratio = __ddiv_rn((double)T, (double)S);
+    uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + lane * K;
+    uint4 *my_x = ws.band_xchg + bi.xoff + (lane - (32 - HL)) * K;
+
+    auto issue = [&](int i) {                                  // whole warp: lane r copies row r
+        const int st = i % NST;
+        const int t0 = i * TT;
+        const int rows = min(TT, T - t0);
+        const uint32_t row_b = (uint32_t)cols * 4u;
+        if (lane == 0) {
+            hfa_mbar_expect_tx(&bar[st], (uint32_t)rows * row_b + TT * (uint32_t)sizeof(float2));
+            hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
+        }
+        __syncwarp();
+        if (lane < rows)
+            hfa_bulk_load(tile0 + st * TILE_FLOATS + lane * W, g_emis + (int64_t)(t0 + lane) * Sp, row_b,
+                          &bar[st]);
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
+        hfa_fence_mbar_init();
+    }
+    __syncwarp();
+    for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
+
+    uint32_t sp_and[K];
+    float jump_cap[K];
+    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
+    const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
+
+    float dp[K], cu[K];
+    uint32_t bits[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        dp[k] = HFA_NEG_INF;
+        cu[k] = HFA_NEG_INF;
+        bits[k] = 0;
+    }
+    const uint32_t tile_sa = hfa_smem_u32(tile0) + (uint32_t)(lane * K) * 4u;
+    const uint32_t edge_sa = hfa_smem_u32(edge0);
+    constexpr uint32_t row_bytes = (uint32_t)W * 4u;
+
+    int st = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        // halo for the NEXT tile = the left neighbour's last 32 states after THIS tile: request the
+        // slots now, look at them when the tile is done (the neighbour normally runs >= 1 tile ahead)
+        const bool need_halo = has_left && i + 1 < n_tiles;
+        const uint32_t tag = (uint32_t)i + 1u;
+        uint4 h[K];
+        if (need_halo && lane < HL) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) h[k] = hfa_ld_slot(left_x + (int64_t)i * 32 + k);
+        }
+        hfa_mbar_wait(&bar[st], phase);
+        const uint32_t tl = tile_sa + (uint32_t)st * (TILE_FLOATS * 4u);
+        const uint32_t et = edge_sa + (uint32_t)st * (TT * 8u);
+        const int rows = min(TT, T - i * TT);
+        uint32_t mbit = 1u;
+        auto frame = [&](int tt, const float (&e)[K], const float2 ed, float (&en)[K], float2 &edn) {
+            hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, en);
+            edn = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
+            if (tt == 0 && i == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int s = first + k;
+                    if (s == 0 || (s == 1 && lead_sp)) {
+                        dp[k] = e[k];
+                        cu[k] = e[k];
+                    }
+                }
+            } else {
+                float stay[K], adv[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float base = __fadd_rn(dp[k], e[k]);
+                    stay[k] = __fadd_rn(base, ed.y);
+                    adv[k] = hfa_advance(__fadd_rn(base, ed.x), cu[k], ratio);
+                }
+                float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
+                float up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
+                // lane 0: nothing to the left of state 0 (band 0) / stale halo edge (other bands)
+                if (lane == 0) {
+                    up1 = HFA_NEG_INF;
+                    up2 = HFA_NEG_INF;
+                }
+                hfa_select<K>(e, stay, adv, up1, up2, sp_and, jump_cap, mbit, mbit << 16, dp, cu, bits);
+            }
+            mbit <<= 1;
+            if constexpr (DUMP) {
+                const int64_t o = m.cell_off + (int64_t)(i * TT + tt) * S;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (owner && first + k < S) dp_dump[o + first + k] = dp[k];
+            }
+        };
+        float ea[K], eb[K];
+        float2 da, db;
+        hfa_lds_row<K>(tl, ea);
+        da = hfa_lds_f2(et);
+        if (rows == TT) {
+#pragma unroll 1
+            for (int tt = 0; tt < TT; tt += 2) {
+                frame(tt, ea, da, eb, db);
+                frame(tt + 1, eb, db, ea, da);
+            }
+        } else {
+            for (int tt = 0; tt < rows; ++tt) {               // last, partial tile
+                frame(tt, ea, da, eb, db);
+#pragma unroll
+                for (int k = 0; k < K; ++k) ea[k] = eb[k];
+                da = db;
+            }
+        }
+        // one backpointer word per owned state per tile
+        if (owner) hfa_store_bits<K>(g_bp + (int64_t)i * Sp + first, bits, first, Sp);
+#pragma unroll
+        for (int k = 0; k < K; ++k) bits[k] = 0;
+        if (has_right && i + 1 < n_tiles && lane >= 32 - HL) {   // publish the right neighbour's halo
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                hfa_st_slot(my_x + (int64_t)i * 32 + k,
+                            make_uint4(__float_as_uint(dp[k]), tag, __float_as_uint(cu[k]), tag));
+        }
+        if (need_halo && lane < HL) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint4 *src = left_x + (int64_t)i * 32 + k;
+                uint32_t spins = 0;
+                while (h[k].y != tag || h[k].w != tag) {
+                    if (++spins > (1u << 26)) __trap();
+                    h[k] = hfa_ld_slot(src);
+                }
+                dp[k] = __uint_as_float(h[k].x);
+                cu[k] = __uint_as_float(h[k].z);
+                hfa_st_slot(src, make_uint4(0u, 0u, 0u, 0u));   // leave the table clean for the next call
+            }
+        }
+        __syncwarp();                                        // every lane is done reading stage `st`
+        if (i + NST < n_tiles) issue(i + NST);
+        if (++st == NST) {
+            st = 0;
+            phase ^= 1u;
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (owner && first + k == S - 1) ws.dp_last[2 * u] = dp[k];
+        if (owner && first + k == S - 2) ws.dp_last[2 * u + 1] = dp[k];
+    }
+}
+
 template <int K>
 cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, float *dp_dump)
 {
@@ -805,4 +1043,35 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
     else { HFA_WAVE_LAUNCH(HFA_CTA_K, 1024); }
 #undef HFA_WAVE_LAUNCH
     return cudaGetLastError();
+}
+
+// banded kernel: items [item_begin, item_begin + n_items) of the plan's band table, one warp each
+template <int K>
+static cudaError_t launch_band(const HfaLaunchCtx &c, int item_begin, int n_items, int32_t *ticket,
+                               float *dp_dump)
+{
+    const size_t smem = hfa_band_smem_bytes<K>();
+    cudaError_t e;
+    if (dp_dump != nullptr) {
+        e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_dp_band_kernel<K, true><<<n_items, 32, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
+    } else {
+        e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hfa_dp_band_kernel<K, false><<<n_items, 32, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
+                               float *dp_dump)
+{
+    if (n_items <= 0) return cudaSuccess;
+    switch (k) {
+        case 2: return launch_band<2>(c, item_begin, n_items, ticket, dp_dump);
+        case 4: return launch_band<4>(c, item_begin, n_items, ticket, dp_dump);
+        case 8: return launch_band<8>(c, item_begin, n_items, ticket, dp_dump);
+        default: return cudaErrorInvalidValue;
+    }
 }

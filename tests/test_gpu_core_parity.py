@@ -11,11 +11,18 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1"], ids=["warp-per-utterance", "latency-routing"])
+@pytest.fixture(params=["0", "1", "2", "2k8", "auto"],
+                ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8", "auto"])
 def routing(request, monkeypatch):
-    """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes),
-    1 = utterances with > 64 states go to the multi-warp kernel (the small-batch default)."""
-    monkeypatch.setenv("HFA_LATENCY_MODE", request.param)
+    """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
+    S > 256 in the CTA kernel; 1 = utterances with > 64 states go to the multi-warp CTA kernel;
+    2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane; auto = the
+    plan's own choice (banded for these small batches)."""
+    if request.param != "auto":
+        monkeypatch.setenv("HFA_LATENCY_MODE", request.param[0])
+        monkeypatch.setenv("HFA_BIG_KERNEL", "band" if request.param[0] == "2" else "cta")
+    if request.param == "2k8":
+        monkeypatch.setenv("HFA_BIG_K", "8")
     return request.param
 
 
@@ -121,8 +128,13 @@ def test_invalid_utterances_get_a_status():
     assert np.array_equal(v["ph_idx_seq"][:v["n_seg"][0]], r["ph_idx_seq"])
 
 
-def test_long_form_c3_stress():
-    """BASELINE config 3: one 10-minute utterance, T=30000, S=2000 (CTA kernel, 1875 word rows)."""
+@pytest.mark.parametrize("big", ["cta", "band2", "band4", "band8"])
+def test_long_form_c3_stress(big, monkeypatch):
+    """BASELINE config 3: one 10-minute utterance, T=30000, S=2000 (1875 word rows): the CTA-per-
+    utterance kernel and the banded kernel with 2 / 4 / 8 states per lane (63 / 21 / 9 warps)."""
+    monkeypatch.setenv("HFA_BIG_KERNEL", "cta" if big == "cta" else "band")
+    if big != "cta":
+        monkeypatch.setenv("HFA_BIG_K", big[4:])
     x = synth_core_inputs(30000, 2000, 63, 31337, "dictionary", planted=True)
     out = run_core_gpu([x["ids"]], [x["prob_log"]], [x["el"]], [x["ne"]], [x["p"]], dump=False)
     r = check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], out[0], x["p"], full=False)
