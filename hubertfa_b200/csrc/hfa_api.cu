@@ -332,7 +332,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 for (int j = 0; j < nb; ++j) {
                     const bool has_right = j + 1 < nb;
                     p->band_items.push_back(HfaBandItem{b, j, has_right ? p->band_xchg_elems : 0});
-                    if (has_right) p->band_xchg_elems += tiles * 32;
+                    if (has_right) p->band_xchg_elems += tiles * 64;
                 }
             }
             p->band_count[which] = (int32_t)p->band_items.size() - p->band_begin[which];

@@ -42,7 +42,7 @@ struct HfaInput {                // per-utterance logits descriptor (changes per
 // consecutive bands of one utterance
 struct HfaBandItem {
     int32_t utt, band;
-    int64_t xoff;                // uint4 index of this band's exchange slots [n_tiles][32] (0 if unused)
+    int64_t xoff;                // uint4 index of this band's exchange slots [n_tiles][32][2] (0 if unused)
 };
 
 // device-side view of the workspace (pointers computed on the host from the plan's layout)
@@ -63,7 +63,7 @@ struct HfaWs {
     float *dp_last;              // end-of-forward scores: [n_utt][2] = dp[T-1][S-1], dp[T-1][S-2]
     const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
     int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
-    uint4 *band_xchg;            // {dp, tag, curr, tag} of a band's last 32 states after every tile;
+    uint4 *band_xchg;            // {dp, tag, p.lo, tag}{p.hi, tag, 0, tag} of a band's last 32 states per tile;
                                  // all-zero between calls (zeroed by hfa_plan_upload, then by its readers)
 };
 

@@ -159,6 +159,82 @@ __device__ __forceinline__ float2 hfa_lds_f2(uint32_t addr)
     return v;
 }
 
+// exchange slot of one state: two 16-byte words {dp bits, tag, p.lo, tag} {p.hi, tag, 0, tag},
+// tag = tile + 1.  Every 8-byte half carries its own tag (8-byte accesses are single-copy atomic),
+// so the reader needs no flag and no fence: a half is valid iff its tag matches.  The reader zeroes
+// a slot after use, so the table is all-zero between calls (zeroed once by hfa_plan_upload).
+__device__ __forceinline__ uint4 hfa_ld_slot(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void hfa_st_slot(uint4 *p, uint4 v)
+{
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// One frame of K states with curr carried as p = f64(curr) * ratio (see above).
+//   e / pe : this frame's emissions and f64(e) * ratio;  ed = {edge_log, not_edge_log}
+//   cap1   : +inf, or -inf where state first-1 does not exist (lane 0)
+//   sp_hi  : 0 for id-0 (SP) states else ~0 -- ANDed into the high word of p: a zero high word makes
+//            p a non-negative subnormal below 2^-1042, which adds to any f64(f32) exactly like +0.0
+template <int K>
+__device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&pe)[K], const float2 ed,
+                                            const uint32_t (&sp_hi)[K], const float (&jump_cap)[K],
+                                            const float cap1, const uint32_t m1, const uint32_t m2,
+                                            float (&dp)[K], double (&p)[K], uint32_t (&bits)[K])
+{
+    float stay[K], adv[K];
+    // the last state's advance score crosses lanes (shuffle): with two states per lane its conversion
+    // chain goes first
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+        const int k = (K <= 2) ? K - 1 - kk : kk;     // measured: descending only pays for K = 2
+        const float base = __fadd_rn(dp[k], e[k]);
+        adv[k] = __double2float_rn(__dadd_rn((double)__fadd_rn(base, ed.x), p[k]));
+        stay[k] = __fadd_rn(base, ed.y);
+    }
+    float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
+    const float up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);   // capped by jump_cap on lane 0
+    up1 = fminf(up1, cap1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float p2 = (k == 0) ? up1 : adv[k - 1];
+        const float p3 = (k == 0) ? up2 : ((k == 1) ? up1 : adv[k - 2]);
+        // alignment_decoder.py:210-228.  Value: max of the three candidates.  Backpointer: strict
+        // '>' scanned in the order stay, +1, +2 (ties keep the earlier candidate).  curr: moved ?
+        // e : max(curr, e), 0 for id-0 states -- all on p.
+        asm("{\n\t"
+            ".reg .pred q1, q2, q3;\n\t"
+            ".reg .f32 j, m;\n\t"
+            ".reg .f64 pn;\n\t"
+            ".reg .b32 lo, hi;\n\t"
+            "min.f32 j, %5, %6;\n\t"
+            "max.f32 m, %4, %3;\n\t"
+            "max.f32 %0, m, j;\n\t"
+            "setp.gt.f32 q1, %3, %4;\n\t"
+            "setp.gt.f32 q2, j, m;\n\t"
+            "@q1 or.b32 %2, %2, %9;\n\t"
+            "@q2 or.b32 %2, %2, %10;\n\t"
+            "or.pred q3, q1, q2;\n\t"
+            "setp.gt.or.f64 q3, %7, %1, q3;\n\t"
+            "selp.f64 pn, %7, %1, q3;\n\t"
+            "mov.b64 {lo, hi}, pn;\n\t"
+            "and.b32 hi, hi, %8;\n\t"
+            "mov.b64 %1, {lo, hi};\n\t"
+            "}"
+            : "=f"(dp[k]), "+d"(p[k]), "+r"(bits[k])
+            : "f"(p2), "f"(stay[k]), "f"(p3), "f"(jump_cap[k]), "d"(pe[k]), "r"(sp_hi[k]), "r"(m1),
+              "r"(m2));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp per utterance
 // ---------------------------------------------------------------------------------------------
@@ -319,6 +395,152 @@ __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
     }
 }
 
+// The same kernel with the recurrence in its "p form" (hfa_frame_p): curr carried as the f64 product
+// f64(curr) * ratio, emissions' products computed one frame ahead, dp' taken with FMNMX.
+template <int K, bool DUMP>
+__device__ __forceinline__ void hfa_dp_warp_body_p(const HfaWs &ws, const int u,
+                                                   float *__restrict__ dp_dump,
+                                                   unsigned char *smem_raw)
+{
+    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
+    constexpr int ROW_MAX = 32 * K;
+    constexpr int TILE_FLOATS = TT * ROW_MAX;
+    float *tile0 = reinterpret_cast<float *>(smem_raw);
+    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + ROW_MAX);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
+
+    const int lane = threadIdx.x & 31;
+    const HfaUtt m = ws.utt[u];
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int first = lane * K;
+    const int n_tiles = (T + TT - 1) / TT;
+    const float *g_emis = ws.emis + m.emis_off;
+    const float2 *g_edge = ws.edge2 + m.edge_off;
+    uint32_t *g_bp = ws.bp + m.bp_off;
+    const double ratio = __ddiv_rn((double)T, (double)S);
+
+    auto issue = [&](int i) {                                  // lane 0 only
+        const int st = i % NST;
+        const int t0 = i * TT;
+        const int rows = min(TT, T - t0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)Sp * 4u;
+        hfa_mbar_expect_tx(&bar[st], bytes + TT * (uint32_t)sizeof(float2));
+        hfa_bulk_load(tile0 + st * TILE_FLOATS, g_emis + (int64_t)t0 * Sp, bytes, &bar[st]);
+        hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
+        hfa_fence_mbar_init();
+        for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
+    }
+    uint32_t sp_hi[K];
+    float jump_cap[K];
+    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_hi, jump_cap);
+    const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
+    const float cap1 = lane == 0 ? HFA_NEG_INF : __uint_as_float(0x7f800000u);
+    __syncwarp();
+
+    float dp[K];
+    double p[K];
+    uint32_t bits[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        dp[k] = HFA_NEG_INF;
+        p[k] = __longlong_as_double(0xfff0000000000000ll);     // curr = -inf
+        bits[k] = 0;
+    }
+    const uint32_t tile_sa = hfa_smem_u32(tile0) + (uint32_t)first * 4u;
+    const uint32_t edge_sa = hfa_smem_u32(edge0);
+    const uint32_t row_bytes = (uint32_t)Sp * 4u;
+    auto dump = [&](int t) {
+        if constexpr (DUMP) {
+            const int64_t o = m.cell_off + (int64_t)t * S;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (first + k < S) dp_dump[o + first + k] = dp[k];
+        }
+    };
+
+    int st = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        hfa_mbar_wait(&bar[st], phase);
+        const uint32_t tl = tile_sa + (uint32_t)st * (TILE_FLOATS * 4u);
+        const uint32_t et = edge_sa + (uint32_t)st * (TT * 8u);
+        const int rows = min(TT, T - i * TT);
+        const int sh = (i & 1) * TT;                         // bit position of this tile's frame 0
+        float ea[K], eb[K];
+        double pa[K], pb[K];
+        float2 da, db;
+        hfa_lds_row<K>(tl, ea);
+        da = hfa_lds_f2(et);
+#pragma unroll
+        for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+        int tt0 = 0;
+        if (i == 0) {
+            // t = 0 (:250-254): state 0 is seeded, and state 1 too behind a leading SP
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int s = first + k;
+                if (s == 0 || (s == 1 && lead_sp)) {
+                    dp[k] = ea[k];
+                    p[k] = pa[k];
+                }
+            }
+            dump(0);
+            tt0 = 1;
+        }
+        if (tt0 == 0 && rows == TT) {
+            uint32_t mbit = 1u << sh;
+            // NOT unrolled further: the merged kernel keeps up to 8 code paths hot per SM and must
+            // fit the instruction cache
+#pragma unroll 1
+            for (int tt = 0; tt < TT; tt += 2) {
+                hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, eb);
+                db = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
+                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, mbit, mbit << 16, dp, p, bits);
+#pragma unroll
+                for (int k = 0; k < K; ++k) pb[k] = __dmul_rn((double)eb[k], ratio);
+                if constexpr (DUMP) dump(i * TT + tt);
+                hfa_lds_row<K>(tl + (uint32_t)(tt + 2) * row_bytes, ea);     // slack row after the last
+                da = hfa_lds_f2(et + (uint32_t)(tt + 2) * 8u);
+                hfa_frame_p<K>(eb, pb, db, sp_hi, jump_cap, cap1, mbit << 1, mbit << 17, dp, p, bits);
+#pragma unroll
+                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+                if constexpr (DUMP) dump(i * TT + tt + 1);
+                mbit <<= 2;
+            }
+        } else {
+            for (int tt = tt0; tt < rows; ++tt) {            // first and last (partial) tile
+                hfa_lds_row<K>(tl + (uint32_t)tt * row_bytes, ea);
+                da = hfa_lds_f2(et + (uint32_t)tt * 8u);
+#pragma unroll
+                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, 1u << (sh + tt), 0x10000u << (sh + tt), dp, p,
+                               bits);
+                dump(i * TT + tt);
+            }
+        }
+        if ((i & 1) || i == n_tiles - 1) {                   // 16 frames done (or the end): flush
+            hfa_store_bits<K>(g_bp + (int64_t)(i >> 1) * Sp + first, bits, first, Sp);
+#pragma unroll
+            for (int k = 0; k < K; ++k) bits[k] = 0;
+        }
+        __syncwarp();                                        // every lane is done reading stage `st`
+        if (lane == 0 && i + NST < n_tiles) issue(i + NST);
+        if (++st == NST) {
+            st = 0;
+            phase ^= 1u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (first + k == S - 1) ws.dp_last[2 * u] = dp[k];
+        if (first + k == S - 2) ws.dp_last[2 * u + 1] = dp[k];
+    }
+}
+
 // one state class per launch (used when the classes are spread over streams)
 template <int K, bool DUMP>
 __global__ void __launch_bounds__(32)
@@ -332,7 +554,7 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
 // the shared memory of the largest class present, the block scheduler sees one globally
 // longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.  WPC warps per
 // CTA (one utterance each, no interaction between them); HFA_DP_WPC=4 packs four per CTA.
-template <bool DUMP, int WPC>
+template <bool DUMP, int WPC, bool PF>
 __global__ void __launch_bounds__(32 * WPC)
 hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int smem_per_warp,
                        float *__restrict__ dp_dump)
@@ -342,6 +564,19 @@ hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int s
     if (item >= n) return;
     unsigned char *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * smem_per_warp;
     const int u = order[item];
+    if constexpr (PF) {
+        switch ((ws.utt[u].Sp + 31) >> 5) {
+            case 1: hfa_dp_warp_body_p<2, DUMP>(ws, u, dp_dump, smem_raw); break;   // K = 1 has no second state to shuffle
+            case 2: hfa_dp_warp_body_p<2, DUMP>(ws, u, dp_dump, smem_raw); break;
+            case 3: hfa_dp_warp_body_p<3, DUMP>(ws, u, dp_dump, smem_raw); break;
+            case 4: hfa_dp_warp_body_p<4, DUMP>(ws, u, dp_dump, smem_raw); break;
+            case 5: hfa_dp_warp_body_p<5, DUMP>(ws, u, dp_dump, smem_raw); break;
+            case 6: hfa_dp_warp_body_p<6, DUMP>(ws, u, dp_dump, smem_raw); break;
+            case 7: hfa_dp_warp_body_p<7, DUMP>(ws, u, dp_dump, smem_raw); break;
+            default: hfa_dp_warp_body_p<8, DUMP>(ws, u, dp_dump, smem_raw); break;
+        }
+        return;
+    }
     switch ((ws.utt[u].Sp + 31) >> 5) {
         case 1: hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw); break;
         case 2: hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw); break;
@@ -676,54 +911,46 @@ hfa_dp_wave_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int 
 //
 // State i at frame t only depends on states i, i-1, i-2 at frame t-1 (alignment_decoder.py:177-202),
 // so over a 16-frame tile a state is a function of the 32 states to its left at the start of the
-// tile.  A band is one warp (its own CTA) that holds a window of W = 32 K consecutive states, K per
+// tile.  A band is one compute warp that holds a window of W = 32 K consecutive states, K per
 // lane; windows of neighbouring bands overlap by 32 states: band b covers [b (W-32), b (W-32) + W).
 // The first 32 states of a window (b > 0) are the HALO: they are recomputed from the left
 // neighbour's values at the start of every tile, go stale from the left edge at two states per
 // frame, and the stale region reaches the first owned state exactly when the tile ends.  After each
-// tile the left band publishes {dp, curr} of its last 32 states (= the halo of its right
-// neighbour) and bumps a flag; neighbours never talk inside a tile, so the bands of one utterance
-// run as a pipeline skewed by 1-2 tiles across SMs instead of a serial chain on one lane set.
+// tile the left band publishes {dp, curr*ratio} of its last 32 states (= the halo of its right
+// neighbour); neighbours never talk inside a tile, so the bands of one utterance run as a pipeline
+// skewed by 1-2 tiles across SMs instead of a serial chain on one lane set.
 //   * small batches (latency regime): K = 2 -- every utterance with more than 64 states becomes
-//     ceil((Sp-32)/32) warps whose per-frame instruction stream is that of the K = 2 warp kernel;
-//   * long phoneme sequences (S > 256, BASELINE config 3): K = 4 -- 2000 states = 21 warps on 21 SMs
-//     instead of one CTA with a barrier per frame.
-// Work items are claimed through an atomic ticket, so a band's left neighbour has always started
-// before the band itself (no reliance on block dispatch order); band 0 never waits.
-// Extra HBM/L2 traffic: 256 B per band per tile each way (0.5 B per owned cell at K = 2).
+//     ceil((Sp-32)/32) warps whose per-frame dependent chain is as short as it gets;
+//   * long phoneme sequences (S > 256, BASELINE config 3): K = 2/4 -- 2000 states = 62/21 warps on
+//     as many SMs instead of one CTA with a barrier per frame.
+// CTA = 2 warps.  Warp 1 is the PRODUCER: it issues the TMA row copies of the emission window
+// (16 bulk copies + the edge pairs per tile, 3 stages, full/empty mbarriers) and polls the left
+// neighbour's exchange slots into shared memory; both complete on the stage's "full" barrier.
+// Warp 0 is the CONSUMER: it only waits on that barrier, runs the recurrence, stores backpointer
+// words and publishes its own last 32 states.  Work items are claimed through an atomic ticket, so
+// a band's left neighbour has always started before the band itself; band 0 never waits.
+//
+// The serial chain per frame is  FADD, FADD, F2F, DADD, F2F, SHFL, 3 x FMNMX  (~85 cycles):
+//   * curr[] is carried as the f64 product p = f64(curr) * ratio.  ratio > 0 and rounding is
+//     monotone, so max(curr, e) * ratio == max(p, f64(e) * ratio) bit for bit, and f64(e) * ratio
+//     only depends on the emission: it is computed one frame ahead, off the chain.
+//   * dp' = max(stay, adv1, adv2) is taken with FMNMX (value identical to the reference's strict-'>'
+//     scan, ties included); the two comparisons that define the backpointer run beside it.
+// Extra HBM/L2 traffic: 1 KB per band per tile each way.
 // ---------------------------------------------------------------------------------------------
-// exchange slot of one state: {dp bits, tag, curr bits, tag}, tag = tile + 1.  Each 8-byte half
-// carries its own tag (8-byte accesses are single-copy atomic), so the reader needs no flag and no
-// fence: a half is valid iff its tag matches.  The reader zeroes a slot after use, so the table is
-// all-zero between calls (it is zeroed once by hfa_plan_upload).
-__device__ __forceinline__ uint4 hfa_ld_slot(const uint4 *p)
-{
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
-__device__ __forceinline__ void hfa_st_slot(uint4 *p, uint4 v)
-{
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-
 constexpr int HFA_BAND_STAGES = 3;
 
 template <int K> constexpr size_t hfa_band_smem_bytes()
 {
-    // [stages x 16 rows x 32K floats][slack row][stages x 16 edge pairs][slack pair][mbarriers][ticket]
+    // [stages x 16 rows x 32K floats][slack row][stages x 16 edge pairs][slack pair]
+    // [stages x 32 halo entries {dp, pad, p}][full, empty mbarriers][ticket]
     return (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 1) * 32 * K * sizeof(float) +
-           (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 1) * sizeof(float2) +
-           HFA_BAND_STAGES * sizeof(uint64_t) + 16;
+           (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 2) * sizeof(float2) +
+           (size_t)HFA_BAND_STAGES * 32 * 16 + 2 * HFA_BAND_STAGES * sizeof(uint64_t) + 16;
 }
 
 template <int K, bool DUMP>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump)
 {
     static_assert(32 % K == 0 && K >= 2, "the halo (32 states) must be a whole number of lanes");
@@ -733,141 +960,185 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tile0 = reinterpret_cast<float *>(smem_raw);
     float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + W);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
-    int *slot = reinterpret_cast<int *>(bar + NST);
+    uint4 *halo0 = reinterpret_cast<uint4 *>(edge0 + NST * TT + 2);   // 16-byte aligned
+    uint64_t *full = reinterpret_cast<uint64_t *>(halo0 + NST * 32);
+    uint64_t *empty = full + NST;
+    int *slot = reinterpret_cast<int *>(empty + NST);
 
-    const int lane = threadIdx.x;
-    if (lane == 0) *slot = (int)atomicInc(reinterpret_cast<unsigned int *>(ticket), gridDim.x - 1);
-    __syncwarp();
-    const int item = item_begin + *slot;                       // wraps back to 0 after the last CTA
+    // Which of the two warps computes?  The warps of a 2-warp CTA land on an aligned pair of warp
+    // slots, and slot % 4 is the scheduler partition, so "warp 0 computes" would put every compute
+    // warp of the SM on partitions 0 and 2 (tools/ubench_warpid.cu).  Swapping the roles in every
+    // other pair spreads them over all four.
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        unsigned hw_slot;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_slot));
+        slot[1] = (int)((hw_slot >> 2) & 1u);
+    }
+    if (threadIdx.x == 0) {
+        *slot = (int)atomicInc(reinterpret_cast<unsigned int *>(ticket), gridDim.x - 1);   // self-resetting
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            hfa_mbar_init(&full[s], 2);          // the copy issuer + the halo relay
+            hfa_mbar_init(&empty[s], 1);         // the compute warp
+        }
+        hfa_fence_mbar_init();
+    }
+    __syncthreads();
+    const int warp = (int)(threadIdx.x >> 5) ^ slot[1];        // 0 = compute, 1 = producer
+    const int item = item_begin + *slot;
     const HfaBandItem bi = ws.band_items[item];
     const int u = bi.utt, band = bi.band;
     const HfaUtt m = ws.utt[u];
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int c0 = band * OWN;                                 // first state of the window
-    const int first = c0 + lane * K;                           // first state of this lane
     const int n_bands = Sp <= W ? 1 : (Sp - 32 + OWN - 1) / OWN;
     const bool has_left = band > 0, has_right = band + 1 < n_bands;
-    const bool owner = !has_left || lane >= HL;                // lanes whose states this band owns
     const int n_tiles = (T + TT - 1) / TT;
-    const int cols = min(W, Sp - c0);                          // window columns that exist (% 4 == 0)
-    const float *g_emis = ws.emis + m.emis_off + c0;
-    const float2 *g_edge = ws.edge2 + m.edge_off;
+
+    if (warp == 1) {
+        // ---------------- producer: TMA row copies + halo relay ----------------
+        const int cols = min(W, Sp - c0);                      // window columns that exist (% 4 == 0)
+        const uint32_t row_b = (uint32_t)cols * 4u;
+        const float *g_emis = ws.emis + m.emis_off + c0;
+        const float2 *g_edge = ws.edge2 + m.edge_off;
+        uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + 2 * lane;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int st = i % NST;
+            if (i >= NST) hfa_mbar_wait(&empty[st], (uint32_t)(((i / NST) - 1) & 1));
+            const int t0 = i * TT;
+            const int rows = min(TT, T - t0);
+            if (lane == 0) {
+                hfa_mbar_expect_tx(&full[st], (uint32_t)rows * row_b + TT * (uint32_t)sizeof(float2));
+                hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &full[st]);
+            }
+            __syncwarp();
+            if (lane < rows)
+                hfa_bulk_load(tile0 + st * TILE_FLOATS + lane * W, g_emis + (int64_t)(t0 + lane) * Sp, row_b,
+                              &full[st]);
+            if (has_left && i > 0) {
+                // the window's first 32 states at the start of tile i = the left band's last 32
+                // after its tile i-1: lane j relays state j
+                uint4 *src = left_x + (int64_t)(i - 1) * 64;
+                const uint32_t tag = (uint32_t)i;
+                uint4 a = hfa_ld_slot(src), b = hfa_ld_slot(src + 1);
+                uint32_t spins = 0;
+                while (a.y != tag || a.w != tag || b.y != tag || b.w != tag) {
+                    if (++spins > (1u << 26)) __trap();
+                    a = hfa_ld_slot(src);
+                    b = hfa_ld_slot(src + 1);
+                }
+                halo0[st * 32 + lane] = make_uint4(a.x, 0u, a.z, b.x);
+                hfa_st_slot(src, make_uint4(0u, 0u, 0u, 0u));   // leave the table clean for the next call
+                hfa_st_slot(src + 1, make_uint4(0u, 0u, 0u, 0u));
+            }
+            __syncwarp();
+            if (lane == 0) hfa_mbar_arrive(&full[st]);
+        }
+        return;
+    }
+
+    // ---------------- consumer: the recurrence ----------------
+    const int first = c0 + lane * K;                           // first state of this lane
+    const bool owner = !has_left || lane >= HL;                // lanes whose states this band owns
     uint32_t *g_bp = ws.bp + m.bp_off;
     const double ratio = __ddiv_rn((double)T, (double)S);
-    uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + lane * K;
-    uint4 *my_x = ws.band_xchg + bi.xoff + (lane - (32 - HL)) * K;
+    uint4 *my_x = ws.band_xchg + bi.xoff + 2 * ((lane - (32 - HL)) * K);
 
-    auto issue = [&](int i) {                                  // whole warp: lane r copies row r
-        const int st = i % NST;
-        const int t0 = i * TT;
-        const int rows = min(TT, T - t0);
-        const uint32_t row_b = (uint32_t)cols * 4u;
-        if (lane == 0) {
-            hfa_mbar_expect_tx(&bar[st], (uint32_t)rows * row_b + TT * (uint32_t)sizeof(float2));
-            hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
-        }
-        __syncwarp();
-        if (lane < rows)
-            hfa_bulk_load(tile0 + st * TILE_FLOATS + lane * W, g_emis + (int64_t)(t0 + lane) * Sp, row_b,
-                          &bar[st]);
-    };
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
-        hfa_fence_mbar_init();
-    }
-    __syncwarp();
-    for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
-
-    uint32_t sp_and[K];
+    uint32_t sp_hi[K];
     float jump_cap[K];
-    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
+    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_hi, jump_cap);
     const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
+    // lane 0: nothing to the left of state 0 (band 0) / stale halo edge (other bands, value unused)
+    const float cap1 = lane == 0 ? HFA_NEG_INF : __uint_as_float(0x7f800000u);
 
-    float dp[K], cu[K];
+    float dp[K];
+    double p[K];
     uint32_t bits[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         dp[k] = HFA_NEG_INF;
-        cu[k] = HFA_NEG_INF;
+        p[k] = __longlong_as_double(0xfff0000000000000ll);     // curr = -inf
         bits[k] = 0;
     }
     const uint32_t tile_sa = hfa_smem_u32(tile0) + (uint32_t)(lane * K) * 4u;
     const uint32_t edge_sa = hfa_smem_u32(edge0);
     constexpr uint32_t row_bytes = (uint32_t)W * 4u;
 
+    auto dump = [&](int t) {
+        if constexpr (DUMP) {
+            const int64_t o = m.cell_off + (int64_t)t * S;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (owner && first + k < S) dp_dump[o + first + k] = dp[k];
+        }
+    };
+
     int st = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_tiles; ++i) {
-        // halo for the NEXT tile = the left neighbour's last 32 states after THIS tile: request the
-        // slots now, look at them when the tile is done (the neighbour normally runs >= 1 tile ahead)
-        const bool need_halo = has_left && i + 1 < n_tiles;
-        const uint32_t tag = (uint32_t)i + 1u;
-        uint4 h[K];
-        if (need_halo && lane < HL) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) h[k] = hfa_ld_slot(left_x + (int64_t)i * 32 + k);
-        }
-        hfa_mbar_wait(&bar[st], phase);
+        hfa_mbar_wait(&full[st], phase);
         const uint32_t tl = tile_sa + (uint32_t)st * (TILE_FLOATS * 4u);
         const uint32_t et = edge_sa + (uint32_t)st * (TT * 8u);
         const int rows = min(TT, T - i * TT);
-        uint32_t mbit = 1u;
-        auto frame = [&](int tt, const float (&e)[K], const float2 ed, float (&en)[K], float2 &edn) {
-            hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, en);
-            edn = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
-            if (tt == 0 && i == 0) {
+        if (has_left && i > 0 && lane < HL) {                 // halo: the left band's values
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int s = first + k;
-                    if (s == 0 || (s == 1 && lead_sp)) {
-                        dp[k] = e[k];
-                        cu[k] = e[k];
-                    }
-                }
-            } else {
-                float stay[K], adv[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float base = __fadd_rn(dp[k], e[k]);
-                    stay[k] = __fadd_rn(base, ed.y);
-                    adv[k] = hfa_advance(__fadd_rn(base, ed.x), cu[k], ratio);
-                }
-                float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
-                float up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
-                // lane 0: nothing to the left of state 0 (band 0) / stale halo edge (other bands)
-                if (lane == 0) {
-                    up1 = HFA_NEG_INF;
-                    up2 = HFA_NEG_INF;
-                }
-                hfa_select<K>(e, stay, adv, up1, up2, sp_and, jump_cap, mbit, mbit << 16, dp, cu, bits);
+            for (int k = 0; k < K; ++k) {
+                const uint4 h = halo0[st * 32 + lane * K + k];
+                dp[k] = __uint_as_float(h.x);
+                p[k] = __hiloint2double((int)h.w, (int)h.z);
             }
-            mbit <<= 1;
-            if constexpr (DUMP) {
-                const int64_t o = m.cell_off + (int64_t)(i * TT + tt) * S;
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (owner && first + k < S) dp_dump[o + first + k] = dp[k];
-            }
-        };
+        }
         float ea[K], eb[K];
+        double pa[K], pb[K];
         float2 da, db;
         hfa_lds_row<K>(tl, ea);
         da = hfa_lds_f2(et);
-        if (rows == TT) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+        int tt0 = 0;
+        if (i == 0) {
+            // t = 0 (:250-254): state 0 is seeded, and state 1 too behind a leading SP; curr keeps
+            // the emission even for an id-0 state until the first step has run
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int s = first + k;
+                if (s == 0 || (s == 1 && lead_sp)) {
+                    dp[k] = ea[k];
+                    p[k] = pa[k];
+                }
+            }
+            dump(0);
+            tt0 = 1;
+        }
+        if (tt0 == 0 && rows == TT) {
+            // full tile: operands of the next frame (emissions, their f64 products, edge pair) are
+            // fetched / converted while the current frame's chain runs; two frames per iteration
+            uint32_t mbit = 1u;
 #pragma unroll 1
             for (int tt = 0; tt < TT; tt += 2) {
-                frame(tt, ea, da, eb, db);
-                frame(tt + 1, eb, db, ea, da);
+                hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, eb);
+                db = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
+                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, mbit, mbit << 16, dp, p, bits);
+#pragma unroll
+                for (int k = 0; k < K; ++k) pb[k] = __dmul_rn((double)eb[k], ratio);
+                if constexpr (DUMP) dump(i * TT + tt);
+                hfa_lds_row<K>(tl + (uint32_t)(tt + 2) * row_bytes, ea);     // slack row after the last
+                da = hfa_lds_f2(et + (uint32_t)(tt + 2) * 8u);
+                hfa_frame_p<K>(eb, pb, db, sp_hi, jump_cap, cap1, mbit << 1, mbit << 17, dp, p, bits);
+#pragma unroll
+                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+                if constexpr (DUMP) dump(i * TT + tt + 1);
+                mbit <<= 2;
             }
         } else {
-            for (int tt = 0; tt < rows; ++tt) {               // last, partial tile
-                frame(tt, ea, da, eb, db);
+            for (int tt = tt0; tt < rows; ++tt) {            // first and last (partial) tile
+                hfa_lds_row<K>(tl + (uint32_t)tt * row_bytes, ea);
+                da = hfa_lds_f2(et + (uint32_t)tt * 8u);
 #pragma unroll
-                for (int k = 0; k < K; ++k) ea[k] = eb[k];
-                da = db;
+                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
+                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, 1u << tt, 0x10000u << tt, dp, p, bits);
+                dump(i * TT + tt);
             }
         }
         // one backpointer word per owned state per tile
@@ -875,27 +1146,16 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
 #pragma unroll
         for (int k = 0; k < K; ++k) bits[k] = 0;
         if (has_right && i + 1 < n_tiles && lane >= 32 - HL) {   // publish the right neighbour's halo
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                hfa_st_slot(my_x + (int64_t)i * 32 + k,
-                            make_uint4(__float_as_uint(dp[k]), tag, __float_as_uint(cu[k]), tag));
-        }
-        if (need_halo && lane < HL) {
+            const uint32_t tag = (uint32_t)i + 1u;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                uint4 *src = left_x + (int64_t)i * 32 + k;
-                uint32_t spins = 0;
-                while (h[k].y != tag || h[k].w != tag) {
-                    if (++spins > (1u << 26)) __trap();
-                    h[k] = hfa_ld_slot(src);
-                }
-                dp[k] = __uint_as_float(h[k].x);
-                cu[k] = __uint_as_float(h[k].z);
-                hfa_st_slot(src, make_uint4(0u, 0u, 0u, 0u));   // leave the table clean for the next call
+                uint4 *dst = my_x + (int64_t)i * 64 + 2 * k;
+                hfa_st_slot(dst, make_uint4(__float_as_uint(dp[k]), tag, (uint32_t)__double2loint(p[k]), tag));
+                hfa_st_slot(dst + 1, make_uint4((uint32_t)__double2hiint(p[k]), tag, 0u, tag));
             }
         }
         __syncwarp();                                        // every lane is done reading stage `st`
-        if (i + NST < n_tiles) issue(i + NST);
+        if (lane == 0) hfa_mbar_arrive(&empty[st]);
         if (++st == NST) {
             st = 0;
             phase ^= 1u;
@@ -931,15 +1191,15 @@ cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, floa
 
 }  // namespace
 
-template <bool DUMP, int WPC>
+template <bool DUMP, int WPC, bool PF>
 static cudaError_t launch_any(const HfaLaunchCtx &c, size_t per_warp, const int32_t *order, int n,
                               float *dp_dump)
 {
-    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, WPC>,
+    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, WPC, PF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(WPC * ((hfa_warp_smem_bytes<8>() + 127) & ~(size_t)127)));
     if (e != cudaSuccess) return e;
-    hfa_dp_warp_any_kernel<DUMP, WPC><<<(n + WPC - 1) / WPC, 32 * WPC, WPC * per_warp, c.stream>>>(
+    hfa_dp_warp_any_kernel<DUMP, WPC, PF><<<(n + WPC - 1) / WPC, 32 * WPC, WPC * per_warp, c.stream>>>(
         c.ws, order, n, (int)per_warp, dp_dump);
     return cudaGetLastError();
 }
@@ -949,7 +1209,7 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
                                    float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    static const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(), hfa_warp_smem_bytes<2>(),
+    static const size_t bytes[9] = {0, hfa_warp_smem_bytes<2>(), hfa_warp_smem_bytes<2>(),
                                     hfa_warp_smem_bytes<3>(), hfa_warp_smem_bytes<4>(),
                                     hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),
                                     hfa_warp_smem_bytes<7>(), hfa_warp_smem_bytes<8>()};
@@ -959,11 +1219,20 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
         const char *e = getenv("HFA_DP_WPC");
         return (e && e[0] == '4') ? 4 : 1;   // measured on B200: 1 warp per CTA is the faster one
     }();
-    if (dp_dump != nullptr)
-        return wpc == 1 ? launch_any<true, 1>(c, per_warp, order, n, dp_dump)
-                        : launch_any<true, 4>(c, per_warp, order, n, dp_dump);
-    return wpc == 1 ? launch_any<false, 1>(c, per_warp, order, n, dp_dump)
-                    : launch_any<false, 4>(c, per_warp, order, n, dp_dump);
+    // HFA_DP_FORM=p selects the p-form body (shorter chain, 111 instead of 96 registers); measured
+    // equal on the machine-filling batch (config 4: 0.472 vs 0.468 ms), so the leaner one is the default
+    static const bool pform = [] {
+        const char *e = getenv("HFA_DP_FORM");
+        return e && e[0] == 'p';
+    }();
+    if (pform) {
+        if (dp_dump != nullptr) return launch_any<true, 1, true>(c, per_warp, order, n, dp_dump);
+        return wpc == 1 ? launch_any<false, 1, true>(c, per_warp, order, n, dp_dump)
+                        : launch_any<false, 4, true>(c, per_warp, order, n, dp_dump);
+    }
+    if (dp_dump != nullptr) return launch_any<true, 1, false>(c, per_warp, order, n, dp_dump);
+    return wpc == 1 ? launch_any<false, 1, false>(c, per_warp, order, n, dp_dump)
+                    : launch_any<false, 4, false>(c, per_warp, order, n, dp_dump);
 }
 
 // order: device pointer to the utterance indices of this class; n: how many
@@ -1055,11 +1324,11 @@ static cudaError_t launch_band(const HfaLaunchCtx &c, int item_begin, int n_item
     if (dp_dump != nullptr) {
         e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hfa_dp_band_kernel<K, true><<<n_items, 32, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
+        hfa_dp_band_kernel<K, true><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
     } else {
         e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hfa_dp_band_kernel<K, false><<<n_items, 32, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
+        hfa_dp_band_kernel<K, false><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
     }
     return cudaGetLastError();
 }
