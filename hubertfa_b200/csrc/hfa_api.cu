@@ -22,7 +22,7 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
-                               float *dp_dump);
+                               bool keep_dp, float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
                                 int64_t max_row_stride, int *n_launched);
 cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype);
@@ -102,7 +102,7 @@ struct hfa_plan {
     // 2 states per lane), [1] long phoneme sequences (S > 256, band_k[1] states per lane)
     std::vector<HfaBandItem> band_items;
     int32_t band_begin[2] = {0, 0}, band_count[2] = {0, 0}, band_k[2] = {2, 4};
-    int64_t band_xchg_elems = 0;
+    int64_t band_xchg_elems = 0, dp_store_elems = 0;
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
     std::vector<int32_t> block_utt;            // [row_blocks[n]]
@@ -111,7 +111,7 @@ struct hfa_plan {
     // byte offsets
     int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
-            o_last = 0, o_band_items = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
+            o_last = 0, o_dpst = 0, o_band_items = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
     std::vector<unsigned char> head;           // host image of the head (without inputs)
     // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
     // aligned base pointers and positive row strides of at most this many elements (TMA path)
@@ -139,6 +139,7 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.rev_idx = reinterpret_cast<int32_t *>(b + p->o_revi);
     w.rev_t = reinterpret_cast<int32_t *>(b + p->o_revt);
     w.dp_last = reinterpret_cast<float *>(b + p->o_last);
+    w.dp_store = reinterpret_cast<float *>(b + p->o_dpst);
     w.band_items = reinterpret_cast<const HfaBandItem *>(b + p->o_band_items);
     w.band_ticket = reinterpret_cast<int32_t *>(b + p->o_band_ticket);
     w.band_xchg = reinterpret_cast<uint4 *>(b + p->o_band_xchg);
@@ -224,6 +225,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             m.emis_off = emis;
             m.edge_off = edge;
             m.bp_off = words;
+            m.dp_off = -1;
             p->frame_off[b] = frames;
             if (st == HFA_UTT_OK) {
                 m.T = t;
@@ -309,26 +311,44 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         }
         std::vector<int32_t> big_band;
         {
-            int big_k = 4;
-            if (const char *e = std::getenv("HFA_BIG_K")) big_k = std::atoi(e);
-            if (big_k != 2 && big_k != 4 && big_k != 8) big_k = 4;
-            p->band_k[1] = big_k;
+            // states per lane of the long-sequence bands: as few as the band budget allows (measured on
+            // config 3: 2.5 ms with 2, 3.8 ms with 4, 9.9 ms with 8, 17 ms in the CTA kernel)
             int big_mode = -1;                               // -1 auto, 0 cta, 1 band
             if (const char *e = std::getenv("HFA_BIG_KERNEL")) big_mode = (e[0] == 'b');
-            int64_t nb = 0;
-            for (int32_t b : lists[HFA_NUM_CLASSES]) nb += n_bands(b, big_k);
-            if (big_mode == 1 || (big_mode == -1 && nb <= band_max)) {
+            auto count = [&](int k) {
+                int64_t nb = 0;
+                for (int32_t b : lists[HFA_NUM_CLASSES]) nb += n_bands(b, k);
+                return nb;
+            };
+            int big_k = 0;
+            if (const char *e = std::getenv("HFA_BIG_K")) big_k = std::atoi(e);
+            if (big_k != 2 && big_k != 4 && big_k != 8) {
+                big_k = 8;
+                for (int k : {2, 4, 8})
+                    if (count(k) <= band_max) { big_k = k; break; }
+            }
+            p->band_k[1] = big_k;
+            if (big_mode == 1 || (big_mode == -1 && count(big_k) <= band_max)) {
                 big_band = lists[HFA_NUM_CLASSES];
                 lists[HFA_NUM_CLASSES].clear();
                 p->class_count[HFA_NUM_CLASSES] = 0;
             }
         }
+        bool keep_dp = true;
+        if (const char *e = std::getenv("HFA_KEEP_DP")) keep_dp = (e[0] != '0');
         auto add_bands = [&](const std::vector<int32_t> &utts, int which) {
             const int k = p->band_k[which];
             p->band_begin[which] = (int32_t)p->band_items.size();
             for (int32_t b : utts) {
                 const int nb = n_bands(b, k);
                 const int64_t tiles = (p->utt[b].T + 15) / 16;
+                // the banded routing is the latency regime: the forward pass also keeps dp (4 B per
+                // cell more HBM traffic, irrelevant there) so that the backtrace reads dp[t, s_t]
+                // instead of re-running the serial chain along the path
+                if (keep_dp) {
+                    p->utt[b].dp_off = p->dp_store_elems;
+                    p->dp_store_elems += (int64_t)p->utt[b].T * p->utt[b].Sp;
+                }
                 for (int j = 0; j < nb; ++j) {
                     const bool has_right = j + 1 < nb;
                     p->band_items.push_back(HfaBandItem{b, j, has_right ? p->band_xchg_elems : 0});
@@ -382,6 +402,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_revi = region(p->total_states * 4);
         p->o_revt = region(p->total_states * 4);
         p->o_last = region((int64_t)n_utt * 8);
+        p->o_dpst = region(p->dp_store_elems * 4);
         p->o_band_ticket = region(p->band_items.empty() ? 0 : 8);
         p->o_band_xchg = region(p->band_xchg_elems * 16);
         p->band_bytes = o - p->o_band_ticket;
@@ -631,10 +652,10 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k == -3)
             e = hfa_launch_dp_band(c, p->band_k[0], p->band_begin[0], p->band_count[0], c.ws.band_ticket,
-                                   dp_dump);
+                                   p->dp_store_elems > 0, dp_dump);
         else if (items[it].k == -4)
             e = hfa_launch_dp_band(c, p->band_k[1], p->band_begin[1], p->band_count[1],
-                                   c.ws.band_ticket + 1, dp_dump);
+                                   c.ws.band_ticket + 1, p->dp_store_elems > 0, dp_dump);
         else if (items[it].k == -2)
             e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else

@@ -148,6 +148,40 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     // 32 frames per round: lanes gather the operands of their frame (software-pipelined: path
     // states two rounds ahead, emissions one round ahead), then the f32/f64 chain itself runs once
     // per frame, uniformly, over operands parked in shared memory.
+    double log_sum = 0.0;
+    if (m.dp_off >= 0) {
+        // the forward pass kept dp for this utterance (banded routing): dp[t, s_t] is a gather, four
+        // frames per lane in flight, no serial chain
+        const float *dps = ws.dp_store + m.dp_off;
+        float carry = 0.0f;                                  // dp_path[-1] := 0 (:286)
+        for (int base = 0; base < T; base += 128) {
+            int stq[4];
+            float dq[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int t = base + 32 * qq + lane;
+                stq[qq] = (t < T) ? path_state[t] : 0;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int t = base + 32 * qq + lane;
+                dq[qq] = (t < T) ? dps[(int64_t)t * Sp + stq[qq]] : 0.0f;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int t = base + 32 * qq + lane;
+                float prev = __shfl_up_sync(0xffffffffu, dq[qq], 1);
+                if (lane == 0) prev = carry;
+                carry = __shfl_sync(0xffffffffu, dq[qq], 31);
+                if (t < T) {
+                    const float fc = expf(__fsub_rn(dq[qq], prev));          // :284-288
+                    if (frame_conf != nullptr) frame_conf[m.frame_off + t] = fc;
+                    if (dp_path != nullptr) dp_path[m.frame_off + t] = dq[qq];
+                    log_sum += (double)logf(__fadd_rn(fc, 1e-6f));           // :97
+                }
+            }
+        }
+    } else {
     const float *emis = ws.emis + m.emis_off;
     const float2 *edge2 = ws.edge2 + m.edge_off;
     const double ratio = __ddiv_rn((double)T, (double)S);
@@ -155,7 +189,6 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     float4 *stage = stage_sm[warp];
     float *dpath = dpath_sm[warp];
     float d = 0.0f, cu = 0.0f, carry_d = 0.0f;          // dp_path[-1] := 0 (:286)
-    double log_sum = 0.0;
     const int n_rounds = (T + 31) >> 5;
     auto load_state = [&](int round) {
         const int t = round * 32 + lane;
@@ -278,6 +311,7 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         st_c = st_d;
         g_cur = g_nxt;
         g_nxt = g_nn;
+    }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) log_sum += __shfl_xor_sync(0xffffffffu, log_sum, o);

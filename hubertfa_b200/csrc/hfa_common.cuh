@@ -21,7 +21,7 @@
 #define HFA_CTA_K 8              // states per thread in the CTA-per-utterance kernel
 #define HFA_NUM_CLASSES 8        // K = 1..8 for the warp kernel (index K-1); class 8 -> CTA kernel
 
-struct HfaUtt {                  // 64 bytes, one per utterance, device copy lives in the workspace
+struct HfaUtt {                  // 80 bytes, one per utterance, device copy lives in the workspace
     int32_t T, S, Sp, status;
     int64_t seg_off;             // into ids / per-segment outputs (ints)
     int64_t emis_off;            // floats, multiple of 4
@@ -29,8 +29,11 @@ struct HfaUtt {                  // 64 bytes, one per utterance, device copy liv
     int64_t bp_off;              // u32 words
     int64_t frame_off;           // frames, unpadded (frame_conf / dp_path / path_state / dense in)
     int64_t cell_off;            // sum of T*S of the previous utterances (dense ragged dumps)
+    int64_t dp_off;              // floats into dp_store ([t][Sp] like emis) when the forward pass keeps
+                                 // dp for this utterance (banded routing), else -1
+    int64_t reserved;
 };
-static_assert(sizeof(HfaUtt) == 64, "HfaUtt must stay 64 bytes");
+static_assert(sizeof(HfaUtt) == 80, "HfaUtt is 80 bytes (16-byte multiple)");
 
 struct HfaInput {                // per-utterance logits descriptor (changes per call)
     const void *frame;
@@ -61,6 +64,7 @@ struct HfaWs {
     int32_t *rev_idx;            // [sum S] segments in backward order
     int32_t *rev_t;              // [sum S]
     float *dp_last;              // end-of-forward scores: [n_utt][2] = dp[T-1][S-1], dp[T-1][S-2]
+    float *dp_store;             // dp[t][s] of the utterances with dp_off >= 0 (small-batch routing only)
     const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
     int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
     uint4 *band_xchg;            // {dp, tag, p.lo, tag}{p.hi, tag, 0, tag} of a band's last 32 states per tile;
@@ -101,6 +105,17 @@ __device__ __forceinline__ void hfa_bulk_load(void *dst_smem, const void *src_gm
         "l"(src_gmem), "r"(bytes), "r"(hfa_smem_u32(bar))
         : "memory");
 }
+// shared -> global bulk copy (TMA store), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void hfa_bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(hfa_smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void hfa_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void hfa_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void hfa_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void hfa_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;

@@ -241,21 +241,20 @@ __device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&
 constexpr int HFA_WARP_TILE = 8;      // frames per TMA stage (two stages = one backpointer word)
 constexpr int HFA_WARP_STAGES = 3;    // the copy of tile i+3 is issued when tile i has been consumed
 
-template <int K> constexpr size_t hfa_warp_smem_bytes()
+template <int K> constexpr size_t hfa_warp_smem_bytes(int nst = HFA_WARP_STAGES)
 {
     // [stages x 8 rows x 32K floats][one slack row: the prefetch of "row 8" of the last stage]
     // [stages x 8 edge pairs][one slack pair][stages mbarriers]
-    return (size_t)(HFA_WARP_STAGES * HFA_WARP_TILE + 1) * 32 * K * sizeof(float) +
-           (size_t)(HFA_WARP_STAGES * HFA_WARP_TILE + 1) * sizeof(float2) +
-           HFA_WARP_STAGES * sizeof(uint64_t);
+    return (size_t)(nst * HFA_WARP_TILE + 1) * 32 * K * sizeof(float) +
+           (size_t)(nst * HFA_WARP_TILE + 1) * sizeof(float2) + nst * sizeof(uint64_t);
 }
 
 template <int K, bool DUMP>
 __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
                                                  float *__restrict__ dp_dump,
-                                                 unsigned char *smem_raw)
+                                                 unsigned char *smem_raw, const int NST = HFA_WARP_STAGES)
 {
-    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
+    constexpr int TT = HFA_WARP_TILE;
     constexpr int ROW_MAX = 32 * K;                       // floats per smem tile row (upper bound)
     constexpr int TILE_FLOATS = TT * ROW_MAX;
     float *tile0 = reinterpret_cast<float *>(smem_raw);
@@ -395,152 +394,6 @@ __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
     }
 }
 
-// The same kernel with the recurrence in its "p form" (hfa_frame_p): curr carried as the f64 product
-// f64(curr) * ratio, emissions' products computed one frame ahead, dp' taken with FMNMX.
-template <int K, bool DUMP>
-__device__ __forceinline__ void hfa_dp_warp_body_p(const HfaWs &ws, const int u,
-                                                   float *__restrict__ dp_dump,
-                                                   unsigned char *smem_raw)
-{
-    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
-    constexpr int ROW_MAX = 32 * K;
-    constexpr int TILE_FLOATS = TT * ROW_MAX;
-    float *tile0 = reinterpret_cast<float *>(smem_raw);
-    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * TILE_FLOATS + ROW_MAX);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
-
-    const int lane = threadIdx.x & 31;
-    const HfaUtt m = ws.utt[u];
-    const int T = m.T, S = m.S, Sp = m.Sp;
-    const int first = lane * K;
-    const int n_tiles = (T + TT - 1) / TT;
-    const float *g_emis = ws.emis + m.emis_off;
-    const float2 *g_edge = ws.edge2 + m.edge_off;
-    uint32_t *g_bp = ws.bp + m.bp_off;
-    const double ratio = __ddiv_rn((double)T, (double)S);
-
-    auto issue = [&](int i) {                                  // lane 0 only
-        const int st = i % NST;
-        const int t0 = i * TT;
-        const int rows = min(TT, T - t0);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)Sp * 4u;
-        hfa_mbar_expect_tx(&bar[st], bytes + TT * (uint32_t)sizeof(float2));
-        hfa_bulk_load(tile0 + st * TILE_FLOATS, g_emis + (int64_t)t0 * Sp, bytes, &bar[st]);
-        hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
-        hfa_fence_mbar_init();
-        for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
-    }
-    uint32_t sp_hi[K];
-    float jump_cap[K];
-    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_hi, jump_cap);
-    const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
-    const float cap1 = lane == 0 ? HFA_NEG_INF : __uint_as_float(0x7f800000u);
-    __syncwarp();
-
-    float dp[K];
-    double p[K];
-    uint32_t bits[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        dp[k] = HFA_NEG_INF;
-        p[k] = __longlong_as_double(0xfff0000000000000ll);     // curr = -inf
-        bits[k] = 0;
-    }
-    const uint32_t tile_sa = hfa_smem_u32(tile0) + (uint32_t)first * 4u;
-    const uint32_t edge_sa = hfa_smem_u32(edge0);
-    const uint32_t row_bytes = (uint32_t)Sp * 4u;
-    auto dump = [&](int t) {
-        if constexpr (DUMP) {
-            const int64_t o = m.cell_off + (int64_t)t * S;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (first + k < S) dp_dump[o + first + k] = dp[k];
-        }
-    };
-
-    int st = 0;
-    uint32_t phase = 0;
-    for (int i = 0; i < n_tiles; ++i) {
-        hfa_mbar_wait(&bar[st], phase);
-        const uint32_t tl = tile_sa + (uint32_t)st * (TILE_FLOATS * 4u);
-        const uint32_t et = edge_sa + (uint32_t)st * (TT * 8u);
-        const int rows = min(TT, T - i * TT);
-        const int sh = (i & 1) * TT;                         // bit position of this tile's frame 0
-        float ea[K], eb[K];
-        double pa[K], pb[K];
-        float2 da, db;
-        hfa_lds_row<K>(tl, ea);
-        da = hfa_lds_f2(et);
-#pragma unroll
-        for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
-        int tt0 = 0;
-        if (i == 0) {
-            // t = 0 (:250-254): state 0 is seeded, and state 1 too behind a leading SP
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int s = first + k;
-                if (s == 0 || (s == 1 && lead_sp)) {
-                    dp[k] = ea[k];
-                    p[k] = pa[k];
-                }
-            }
-            dump(0);
-            tt0 = 1;
-        }
-        if (tt0 == 0 && rows == TT) {
-            uint32_t mbit = 1u << sh;
-            // NOT unrolled further: the merged kernel keeps up to 8 code paths hot per SM and must
-            // fit the instruction cache
-#pragma unroll 1
-            for (int tt = 0; tt < TT; tt += 2) {
-                hfa_lds_row<K>(tl + (uint32_t)(tt + 1) * row_bytes, eb);
-                db = hfa_lds_f2(et + (uint32_t)(tt + 1) * 8u);
-                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, mbit, mbit << 16, dp, p, bits);
-#pragma unroll
-                for (int k = 0; k < K; ++k) pb[k] = __dmul_rn((double)eb[k], ratio);
-                if constexpr (DUMP) dump(i * TT + tt);
-                hfa_lds_row<K>(tl + (uint32_t)(tt + 2) * row_bytes, ea);     // slack row after the last
-                da = hfa_lds_f2(et + (uint32_t)(tt + 2) * 8u);
-                hfa_frame_p<K>(eb, pb, db, sp_hi, jump_cap, cap1, mbit << 1, mbit << 17, dp, p, bits);
-#pragma unroll
-                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
-                if constexpr (DUMP) dump(i * TT + tt + 1);
-                mbit <<= 2;
-            }
-        } else {
-            for (int tt = tt0; tt < rows; ++tt) {            // first and last (partial) tile
-                hfa_lds_row<K>(tl + (uint32_t)tt * row_bytes, ea);
-                da = hfa_lds_f2(et + (uint32_t)tt * 8u);
-#pragma unroll
-                for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
-                hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, 1u << (sh + tt), 0x10000u << (sh + tt), dp, p,
-                               bits);
-                dump(i * TT + tt);
-            }
-        }
-        if ((i & 1) || i == n_tiles - 1) {                   // 16 frames done (or the end): flush
-            hfa_store_bits<K>(g_bp + (int64_t)(i >> 1) * Sp + first, bits, first, Sp);
-#pragma unroll
-            for (int k = 0; k < K; ++k) bits[k] = 0;
-        }
-        __syncwarp();                                        // every lane is done reading stage `st`
-        if (lane == 0 && i + NST < n_tiles) issue(i + NST);
-        if (++st == NST) {
-            st = 0;
-            phase ^= 1u;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if (first + k == S - 1) ws.dp_last[2 * u] = dp[k];
-        if (first + k == S - 2) ws.dp_last[2 * u + 1] = dp[k];
-    }
-}
-
 // one state class per launch (used when the classes are spread over streams)
 template <int K, bool DUMP>
 __global__ void __launch_bounds__(32)
@@ -554,38 +407,27 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
 // the shared memory of the largest class present, the block scheduler sees one globally
 // longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.  WPC warps per
 // CTA (one utterance each, no interaction between them); HFA_DP_WPC=4 packs four per CTA.
-template <bool DUMP, int WPC, bool PF>
-__global__ void __launch_bounds__(32 * WPC)
-hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int smem_per_warp,
+template <bool DUMP, int MAXK>
+__global__ void __launch_bounds__(32)
+hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int nst,
                        float *__restrict__ dp_dump)
 {
-    extern __shared__ __align__(128) unsigned char smem_all[];
-    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    // MAXK = largest states-per-lane class in this launch: the register allocation (and with it the
+    // number of resident warps per SM) follows the widest code path that can actually run
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int item = blockIdx.x;
     if (item >= n) return;
-    unsigned char *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * smem_per_warp;
     const int u = order[item];
-    if constexpr (PF) {
-        switch ((ws.utt[u].Sp + 31) >> 5) {
-            case 1: hfa_dp_warp_body_p<2, DUMP>(ws, u, dp_dump, smem_raw); break;   // K = 1 has no second state to shuffle
-            case 2: hfa_dp_warp_body_p<2, DUMP>(ws, u, dp_dump, smem_raw); break;
-            case 3: hfa_dp_warp_body_p<3, DUMP>(ws, u, dp_dump, smem_raw); break;
-            case 4: hfa_dp_warp_body_p<4, DUMP>(ws, u, dp_dump, smem_raw); break;
-            case 5: hfa_dp_warp_body_p<5, DUMP>(ws, u, dp_dump, smem_raw); break;
-            case 6: hfa_dp_warp_body_p<6, DUMP>(ws, u, dp_dump, smem_raw); break;
-            case 7: hfa_dp_warp_body_p<7, DUMP>(ws, u, dp_dump, smem_raw); break;
-            default: hfa_dp_warp_body_p<8, DUMP>(ws, u, dp_dump, smem_raw); break;
-        }
-        return;
-    }
-    switch ((ws.utt[u].Sp + 31) >> 5) {
-        case 1: hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 2: hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 3: hfa_dp_warp_body<3, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 4: hfa_dp_warp_body<4, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 5: hfa_dp_warp_body<5, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 6: hfa_dp_warp_body<6, DUMP>(ws, u, dp_dump, smem_raw); break;
-        case 7: hfa_dp_warp_body<7, DUMP>(ws, u, dp_dump, smem_raw); break;
-        default: hfa_dp_warp_body<8, DUMP>(ws, u, dp_dump, smem_raw); break;
+    const int k = (ws.utt[u].Sp + 31) >> 5;
+    if (k <= 1) hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw, nst);
+    else if (k == 2) hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw, nst);
+    if constexpr (MAXK >= 3) { if (k == 3) hfa_dp_warp_body<3, DUMP>(ws, u, dp_dump, smem_raw, nst); }
+    if constexpr (MAXK >= 4) { if (k == 4) hfa_dp_warp_body<4, DUMP>(ws, u, dp_dump, smem_raw, nst); }
+    if constexpr (MAXK >= 5) { if (k == 5) hfa_dp_warp_body<5, DUMP>(ws, u, dp_dump, smem_raw, nst); }
+    if constexpr (MAXK >= 6) { if (k == 6) hfa_dp_warp_body<6, DUMP>(ws, u, dp_dump, smem_raw, nst); }
+    if constexpr (MAXK >= 8) {
+        if (k == 7) hfa_dp_warp_body<7, DUMP>(ws, u, dp_dump, smem_raw, nst);
+        if (k >= 8) hfa_dp_warp_body<8, DUMP>(ws, u, dp_dump, smem_raw, nst);
     }
 }
 
@@ -949,7 +791,7 @@ template <int K> constexpr size_t hfa_band_smem_bytes()
            (size_t)HFA_BAND_STAGES * 32 * 16 + 2 * HFA_BAND_STAGES * sizeof(uint64_t) + 16;
 }
 
-template <int K, bool DUMP>
+template <int K, bool DUMP, bool KEEP>
 __global__ void __launch_bounds__(64)
 hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump)
 {
@@ -1003,9 +845,26 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         const float *g_emis = ws.emis + m.emis_off + c0;
         const float2 *g_edge = ws.edge2 + m.edge_off;
         uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + 2 * lane;
-        for (int i = 0; i < n_tiles; ++i) {
+        // dp store: the compute warp leaves dp[t][.] of a tile in the stage it has just consumed (in
+        // place of the emissions); before the stage is refilled its owned columns go out as one
+        // bulk store per frame row.
+        const int own0 = has_left ? 32 : 0;                    // first owned column of the window
+        float *g_dp = (KEEP && m.dp_off >= 0 && cols > own0) ? ws.dp_store + m.dp_off + c0 + own0 : nullptr;
+        const uint32_t own_b = (uint32_t)(cols - own0) * 4u;
+        for (int i = 0; i < n_tiles + NST; ++i) {
             const int st = i % NST;
-            if (i >= NST) hfa_mbar_wait(&empty[st], (uint32_t)(((i / NST) - 1) & 1));
+            if (i >= NST) {
+                hfa_mbar_wait(&empty[st], (uint32_t)(((i / NST) - 1) & 1));
+                const int j = i - NST;                         // the tile that sat in this stage
+                if (g_dp != nullptr && lane < min(TT, T - j * TT)) {
+                    hfa_bulk_store(g_dp + (int64_t)(j * TT + lane) * Sp, tile0 + st * TILE_FLOATS + lane * W + own0,
+                                   own_b);
+                    hfa_bulk_commit();
+                    hfa_bulk_wait_read();                      // the stage may be overwritten
+                }
+                __syncwarp();
+            }
+            if (i >= n_tiles) continue;
             const int t0 = i * TT;
             const int rows = min(TT, T - t0);
             if (lane == 0) {
@@ -1035,6 +894,7 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
             __syncwarp();
             if (lane == 0) hfa_mbar_arrive(&full[st]);
         }
+        hfa_bulk_wait_all();
         return;
     }
 
@@ -1065,7 +925,25 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     const uint32_t edge_sa = hfa_smem_u32(edge0);
     constexpr uint32_t row_bytes = (uint32_t)W * 4u;
 
-    auto dump = [&](int t) {
+    // dp[t][.] replaces the emissions of frame t in the stage (picked up by the producer warp)
+    constexpr bool keep = KEEP;      // compiled out when the plan keeps no dp: even a predicated-off store
+                                     // in the frame loop costs 8 % (measured)
+    auto put = [&](uint32_t row_sa, int t) {
+        if (keep) {
+            if constexpr (K % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < K / 4; ++q)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_sa + 16u * q), "f"(dp[4 * q]),
+                                 "f"(dp[4 * q + 1]), "f"(dp[4 * q + 2]), "f"(dp[4 * q + 3])
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < K / 2; ++q)
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_sa + 8u * q), "f"(dp[2 * q]),
+                                 "f"(dp[2 * q + 1])
+                                 : "memory");
+            }
+        }
         if constexpr (DUMP) {
             const int64_t o = m.cell_off + (int64_t)t * S;
 #pragma unroll
@@ -1108,7 +986,7 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                     p[k] = pa[k];
                 }
             }
-            dump(0);
+            put(tl, 0);
             tt0 = 1;
         }
         if (tt0 == 0 && rows == TT) {
@@ -1122,13 +1000,13 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                 hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, mbit, mbit << 16, dp, p, bits);
 #pragma unroll
                 for (int k = 0; k < K; ++k) pb[k] = __dmul_rn((double)eb[k], ratio);
-                if constexpr (DUMP) dump(i * TT + tt);
+                put(tl + (uint32_t)tt * row_bytes, i * TT + tt);
                 hfa_lds_row<K>(tl + (uint32_t)(tt + 2) * row_bytes, ea);     // slack row after the last
                 da = hfa_lds_f2(et + (uint32_t)(tt + 2) * 8u);
                 hfa_frame_p<K>(eb, pb, db, sp_hi, jump_cap, cap1, mbit << 1, mbit << 17, dp, p, bits);
 #pragma unroll
                 for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
-                if constexpr (DUMP) dump(i * TT + tt + 1);
+                put(tl + (uint32_t)(tt + 1) * row_bytes, i * TT + tt + 1);
                 mbit <<= 2;
             }
         } else {
@@ -1138,7 +1016,7 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
 #pragma unroll
                 for (int k = 0; k < K; ++k) pa[k] = __dmul_rn((double)ea[k], ratio);
                 hfa_frame_p<K>(ea, pa, da, sp_hi, jump_cap, cap1, 1u << tt, 0x10000u << tt, dp, p, bits);
-                dump(i * TT + tt);
+                put(tl + (uint32_t)tt * row_bytes, i * TT + tt);
             }
         }
         // one backpointer word per owned state per tile
@@ -1154,7 +1032,8 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                 hfa_st_slot(dst + 1, make_uint4((uint32_t)__double2hiint(p[k]), tag, 0u, tag));
             }
         }
-        __syncwarp();                                        // every lane is done reading stage `st`
+        if (keep) hfa_fence_async_smem();                    // dp rows -> visible to the bulk store
+        __syncwarp();                                        // every lane is done with stage `st`
         if (lane == 0) hfa_mbar_arrive(&empty[st]);
         if (++st == NST) {
             st = 0;
@@ -1191,16 +1070,14 @@ cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, floa
 
 }  // namespace
 
-template <bool DUMP, int WPC, bool PF>
-static cudaError_t launch_any(const HfaLaunchCtx &c, size_t per_warp, const int32_t *order, int n,
+template <bool DUMP, int MAXK>
+static cudaError_t launch_any(const HfaLaunchCtx &c, size_t smem, int nst, const int32_t *order, int n,
                               float *dp_dump)
 {
-    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, WPC, PF>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(WPC * ((hfa_warp_smem_bytes<8>() + 127) & ~(size_t)127)));
+    cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, MAXK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hfa_dp_warp_any_kernel<DUMP, WPC, PF><<<(n + WPC - 1) / WPC, 32 * WPC, WPC * per_warp, c.stream>>>(
-        c.ws, order, n, (int)per_warp, dp_dump);
+    hfa_dp_warp_any_kernel<DUMP, MAXK><<<n, 32, smem, c.stream>>>(c.ws, order, n, nst, dp_dump);
     return cudaGetLastError();
 }
 
@@ -1209,30 +1086,24 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
                                    float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    static const size_t bytes[9] = {0, hfa_warp_smem_bytes<2>(), hfa_warp_smem_bytes<2>(),
-                                    hfa_warp_smem_bytes<3>(), hfa_warp_smem_bytes<4>(),
-                                    hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),
-                                    hfa_warp_smem_bytes<7>(), hfa_warp_smem_bytes<8>()};
     if (max_k < 1 || max_k > 8) return cudaErrorInvalidValue;
-    const size_t per_warp = (bytes[max_k] + 127) & ~(size_t)127;
-    static const int wpc = [] {
-        const char *e = getenv("HFA_DP_WPC");
-        return (e && e[0] == '4') ? 4 : 1;   // measured on B200: 1 warp per CTA is the faster one
+    static const int nst = [] {              // emission stages per warp (8 frames each)
+        const char *e = getenv("HFA_DP_STAGES");
+        const int v = e ? atoi(e) : HFA_WARP_STAGES;
+        return v >= 2 && v <= 4 ? v : HFA_WARP_STAGES;
     }();
-    // HFA_DP_FORM=p selects the p-form body (shorter chain, 111 instead of 96 registers); measured
-    // equal on the machine-filling batch (config 4: 0.472 vs 0.468 ms), so the leaner one is the default
-    static const bool pform = [] {
-        const char *e = getenv("HFA_DP_FORM");
-        return e && e[0] == 'p';
-    }();
-    if (pform) {
-        if (dp_dump != nullptr) return launch_any<true, 1, true>(c, per_warp, order, n, dp_dump);
-        return wpc == 1 ? launch_any<false, 1, true>(c, per_warp, order, n, dp_dump)
-                        : launch_any<false, 4, true>(c, per_warp, order, n, dp_dump);
-    }
-    if (dp_dump != nullptr) return launch_any<true, 1, false>(c, per_warp, order, n, dp_dump);
-    return wpc == 1 ? launch_any<false, 1, false>(c, per_warp, order, n, dp_dump)
-                    : launch_any<false, 4, false>(c, per_warp, order, n, dp_dump);
+    const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(nst), hfa_warp_smem_bytes<2>(nst),
+                             hfa_warp_smem_bytes<3>(nst), hfa_warp_smem_bytes<4>(nst),
+                             hfa_warp_smem_bytes<5>(nst), hfa_warp_smem_bytes<6>(nst),
+                             hfa_warp_smem_bytes<7>(nst), hfa_warp_smem_bytes<8>(nst)};
+    const size_t smem = (bytes[max_k] + 127) & ~(size_t)127;
+    if (dp_dump != nullptr) return launch_any<true, 8>(c, smem, nst, order, n, dp_dump);
+    if (max_k <= 2) return launch_any<false, 2>(c, smem, nst, order, n, dp_dump);
+    if (max_k == 3) return launch_any<false, 3>(c, smem, nst, order, n, dp_dump);
+    if (max_k == 4) return launch_any<false, 4>(c, smem, nst, order, n, dp_dump);
+    if (max_k == 5) return launch_any<false, 5>(c, smem, nst, order, n, dp_dump);
+    if (max_k == 6) return launch_any<false, 6>(c, smem, nst, order, n, dp_dump);
+    return launch_any<false, 8>(c, smem, nst, order, n, dp_dump);
 }
 
 // order: device pointer to the utterance indices of this class; n: how many
@@ -1314,33 +1185,36 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
     return cudaGetLastError();
 }
 
-// banded kernel: items [item_begin, item_begin + n_items) of the plan's band table, one warp each
-template <int K>
+// banded kernel: items [item_begin, item_begin + n_items) of the plan's band table, one CTA each
+template <int K, bool DUMP, bool KEEP>
 static cudaError_t launch_band(const HfaLaunchCtx &c, int item_begin, int n_items, int32_t *ticket,
                                float *dp_dump)
 {
     const size_t smem = hfa_band_smem_bytes<K>();
-    cudaError_t e;
-    if (dp_dump != nullptr) {
-        e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hfa_dp_band_kernel<K, true><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
-    } else {
-        e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hfa_dp_band_kernel<K, false><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
-    }
+    cudaError_t e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, DUMP, KEEP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hfa_dp_band_kernel<K, DUMP, KEEP><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
     return cudaGetLastError();
 }
 
+// keep_dp: the plan reserved a dp store for the utterances of this list (all or none)
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
-                               float *dp_dump)
+                               bool keep_dp, float *dp_dump)
 {
     if (n_items <= 0) return cudaSuccess;
+#define HFA_BAND_CASE(KK)                                                                           \
+    case KK:                                                                                        \
+        if (dp_dump != nullptr)                                                                     \
+            return keep_dp ? launch_band<KK, true, true>(c, item_begin, n_items, ticket, dp_dump)   \
+                           : launch_band<KK, true, false>(c, item_begin, n_items, ticket, dp_dump); \
+        return keep_dp ? launch_band<KK, false, true>(c, item_begin, n_items, ticket, dp_dump)      \
+                       : launch_band<KK, false, false>(c, item_begin, n_items, ticket, dp_dump)
     switch (k) {
-        case 2: return launch_band<2>(c, item_begin, n_items, ticket, dp_dump);
-        case 4: return launch_band<4>(c, item_begin, n_items, ticket, dp_dump);
-        case 8: return launch_band<8>(c, item_begin, n_items, ticket, dp_dump);
+        HFA_BAND_CASE(2);
+        HFA_BAND_CASE(4);
+        HFA_BAND_CASE(8);
         default: return cudaErrorInvalidValue;
     }
+#undef HFA_BAND_CASE
 }

@@ -11,18 +11,22 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1", "2", "2k8", "auto"],
-                ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8", "auto"])
+@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "auto"],
+                ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
+                     "banded-no-dp-store", "auto"])
 def routing(request, monkeypatch):
     """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
     S > 256 in the CTA kernel; 1 = utterances with > 64 states go to the multi-warp CTA kernel;
-    2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane; auto = the
-    plan's own choice (banded for these small batches)."""
+    2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane, the backtrace
+    reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path; auto = the plan's
+    own choice (banded with 2 states per lane for these small batches)."""
     if request.param != "auto":
         monkeypatch.setenv("HFA_LATENCY_MODE", request.param[0])
         monkeypatch.setenv("HFA_BIG_KERNEL", "band" if request.param[0] == "2" else "cta")
-    if request.param == "2k8":
-        monkeypatch.setenv("HFA_BIG_K", "8")
+    if request.param in ("2k4", "2k8"):
+        monkeypatch.setenv("HFA_BIG_K", request.param[2])
+    if request.param == "2nk":
+        monkeypatch.setenv("HFA_KEEP_DP", "0")
     return request.param
 
 

@@ -1,0 +1,17 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_core_parity.py -x -q > gpurun_out/t_band.log 2>&1; echo "rc=$?" >> gpurun_out/t_band.log
+tail -3 gpurun_out/t_band.log
+timeout 300 python bench.py --no-cpu --steps 100 > gpurun_out/bench_c2_a.json 2> gpurun_out/bench_c2_a.err
+HFA_KEEP_DP=0 timeout 300 python bench.py --no-cpu --no-extra --steps 100 > gpurun_out/bench_c2_b.json 2> gpurun_out/bench_c2_b.err
+HFA_BIG_K=2 timeout 300 python bench.py --workload c3 --no-cpu --steps 20 > gpurun_out/bench_c3_a.json 2> gpurun_out/bench_c3_a.err
+HFA_BIG_K=2 HFA_KEEP_DP=0 timeout 300 python bench.py --workload c3 --no-cpu --steps 20 > gpurun_out/bench_c3_b.json 2> gpurun_out/bench_c3_b.err
+timeout 300 python bench.py --workload c1 --no-cpu --steps 100 > gpurun_out/bench_c1_a.json 2> gpurun_out/bench_c1_a.err
+python - <<'PY'
+import json
+for f in ["c2_a","c2_b","c3_a","c3_b","c1_a"]:
+    try:
+        d=json.loads(open(f"gpurun_out/bench_{f}.json").read().strip().splitlines()[-1])
+        print(f, "ms/step %.4f"%d["ms_per_step"], d["roofline"]["stage_ms"], "e2e ms %.3f"%d["e2e"]["ms_per_step"])
+        if "extra" in d: print("   c4", "ms/step %.4f"%d["extra"]["c4"]["ms_per_step"], d["extra"]["c4"]["roofline"]["stage_ms"])
+    except Exception as e: print(f, "ERR", e)
+PY
