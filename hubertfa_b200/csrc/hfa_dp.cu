@@ -20,6 +20,7 @@
 //
 // HBM traffic per DP cell: 4 B emission read + 2 bits backpointer write (+ 8 B per frame of edge
 // logs) = the 4.25 B/cell "algorithmic bytes" of DESIGN.md.
+#include <algorithm>
 #include <cstdlib>
 
 #include "hfa_common.cuh"
@@ -241,8 +242,9 @@ __device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&
 constexpr int HFA_WARP_TILE = 8;      // frames per TMA stage (two stages = one backpointer word)
 constexpr int HFA_WARP_STAGES = 3;    // the copy of tile i+3 is issued when tile i has been consumed
 
-template <int K> constexpr size_t hfa_warp_smem_bytes(int nst = HFA_WARP_STAGES)
+template <int K> constexpr size_t hfa_warp_smem_bytes()
 {
+    constexpr int nst = HFA_WARP_STAGES;
     // [stages x 8 rows x 32K floats][one slack row: the prefetch of "row 8" of the last stage]
     // [stages x 8 edge pairs][one slack pair][stages mbarriers]
     return (size_t)(nst * HFA_WARP_TILE + 1) * 32 * K * sizeof(float) +
@@ -252,9 +254,9 @@ template <int K> constexpr size_t hfa_warp_smem_bytes(int nst = HFA_WARP_STAGES)
 template <int K, bool DUMP>
 __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
                                                  float *__restrict__ dp_dump,
-                                                 unsigned char *smem_raw, const int NST = HFA_WARP_STAGES)
+                                                 unsigned char *smem_raw)
 {
-    constexpr int TT = HFA_WARP_TILE;
+    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
     constexpr int ROW_MAX = 32 * K;                       // floats per smem tile row (upper bound)
     constexpr int TILE_FLOATS = TT * ROW_MAX;
     float *tile0 = reinterpret_cast<float *>(smem_raw);
@@ -409,7 +411,7 @@ hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restric
 // CTA (one utterance each, no interaction between them); HFA_DP_WPC=4 packs four per CTA.
 template <bool DUMP, int MAXK>
 __global__ void __launch_bounds__(32)
-hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int nst,
+hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n,
                        float *__restrict__ dp_dump)
 {
     // MAXK = largest states-per-lane class in this launch: the register allocation (and with it the
@@ -419,15 +421,15 @@ hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, int n
     if (item >= n) return;
     const int u = order[item];
     const int k = (ws.utt[u].Sp + 31) >> 5;
-    if (k <= 1) hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw, nst);
-    else if (k == 2) hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw, nst);
-    if constexpr (MAXK >= 3) { if (k == 3) hfa_dp_warp_body<3, DUMP>(ws, u, dp_dump, smem_raw, nst); }
-    if constexpr (MAXK >= 4) { if (k == 4) hfa_dp_warp_body<4, DUMP>(ws, u, dp_dump, smem_raw, nst); }
-    if constexpr (MAXK >= 5) { if (k == 5) hfa_dp_warp_body<5, DUMP>(ws, u, dp_dump, smem_raw, nst); }
-    if constexpr (MAXK >= 6) { if (k == 6) hfa_dp_warp_body<6, DUMP>(ws, u, dp_dump, smem_raw, nst); }
+    if (k <= 1) hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw);
+    else if (k == 2) hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw);
+    if constexpr (MAXK >= 3) { if (k == 3) hfa_dp_warp_body<3, DUMP>(ws, u, dp_dump, smem_raw); }
+    if constexpr (MAXK >= 4) { if (k == 4) hfa_dp_warp_body<4, DUMP>(ws, u, dp_dump, smem_raw); }
+    if constexpr (MAXK >= 5) { if (k == 5) hfa_dp_warp_body<5, DUMP>(ws, u, dp_dump, smem_raw); }
+    if constexpr (MAXK >= 6) { if (k == 6) hfa_dp_warp_body<6, DUMP>(ws, u, dp_dump, smem_raw); }
     if constexpr (MAXK >= 8) {
-        if (k == 7) hfa_dp_warp_body<7, DUMP>(ws, u, dp_dump, smem_raw, nst);
-        if (k >= 8) hfa_dp_warp_body<8, DUMP>(ws, u, dp_dump, smem_raw, nst);
+        if (k == 7) hfa_dp_warp_body<7, DUMP>(ws, u, dp_dump, smem_raw);
+        if (k >= 8) hfa_dp_warp_body<8, DUMP>(ws, u, dp_dump, smem_raw);
     }
 }
 
@@ -1071,13 +1073,12 @@ cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, floa
 }  // namespace
 
 template <bool DUMP, int MAXK>
-static cudaError_t launch_any(const HfaLaunchCtx &c, size_t smem, int nst, const int32_t *order, int n,
-                              float *dp_dump)
+static cudaError_t launch_any(const HfaLaunchCtx &c, size_t smem, const int32_t *order, int n, float *dp_dump)
 {
     cudaError_t e = cudaFuncSetAttribute(hfa_dp_warp_any_kernel<DUMP, MAXK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hfa_dp_warp_any_kernel<DUMP, MAXK><<<n, 32, smem, c.stream>>>(c.ws, order, n, nst, dp_dump);
+    hfa_dp_warp_any_kernel<DUMP, MAXK><<<n, 32, smem, c.stream>>>(c.ws, order, n, dp_dump);
     return cudaGetLastError();
 }
 
@@ -1087,23 +1088,19 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
 {
     if (n <= 0) return cudaSuccess;
     if (max_k < 1 || max_k > 8) return cudaErrorInvalidValue;
-    static const int nst = [] {              // emission stages per warp (8 frames each)
-        const char *e = getenv("HFA_DP_STAGES");
-        const int v = e ? atoi(e) : HFA_WARP_STAGES;
-        return v >= 2 && v <= 4 ? v : HFA_WARP_STAGES;
-    }();
-    const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(nst), hfa_warp_smem_bytes<2>(nst),
-                             hfa_warp_smem_bytes<3>(nst), hfa_warp_smem_bytes<4>(nst),
-                             hfa_warp_smem_bytes<5>(nst), hfa_warp_smem_bytes<6>(nst),
-                             hfa_warp_smem_bytes<7>(nst), hfa_warp_smem_bytes<8>(nst)};
-    const size_t smem = (bytes[max_k] + 127) & ~(size_t)127;
-    if (dp_dump != nullptr) return launch_any<true, 8>(c, smem, nst, order, n, dp_dump);
-    if (max_k <= 2) return launch_any<false, 2>(c, smem, nst, order, n, dp_dump);
-    if (max_k == 3) return launch_any<false, 3>(c, smem, nst, order, n, dp_dump);
-    if (max_k == 4) return launch_any<false, 4>(c, smem, nst, order, n, dp_dump);
-    if (max_k == 5) return launch_any<false, 5>(c, smem, nst, order, n, dp_dump);
-    if (max_k == 6) return launch_any<false, 6>(c, smem, nst, order, n, dp_dump);
-    return launch_any<false, 8>(c, smem, nst, order, n, dp_dump);
+    static const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(), hfa_warp_smem_bytes<2>(),
+                                    hfa_warp_smem_bytes<3>(), hfa_warp_smem_bytes<4>(),
+                                    hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),
+                                    hfa_warp_smem_bytes<7>(), hfa_warp_smem_bytes<8>()};
+    size_t smem = (bytes[max_k] + 127) & ~(size_t)127;
+    // HFA_DP_WARPS_PER_SM=n caps the resident warps per SM by padding the shared-memory request
+    // (experiment knob; measured on config 4: flat from 13 warps per SM upwards)
+    static const int cap = [] { const char *e = getenv("HFA_DP_WARPS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (cap > 0) smem = std::max(smem, ((size_t)(227 * 1024) / (size_t)cap - 1024) & ~(size_t)127);
+    // (register-leaner variants compiled for the largest class present -- 72 registers for K <= 5 --
+    // and 2 instead of 3 emission stages were measured on config 4: no gain, 0.465 vs 0.459 ms)
+    if (dp_dump != nullptr) return launch_any<true, 8>(c, smem, order, n, dp_dump);
+    return launch_any<false, 8>(c, smem, order, n, dp_dump);
 }
 
 // order: device pointer to the utterance indices of this class; n: how many
