@@ -249,6 +249,18 @@ def main():
             set_inputs(plan, ws, head)
         torch.cuda.synchronize()
         dt = _lib.DTYPE_F32
+        # small batches: stages 1+2 run as ONE fused pass (emissions computed inside the DP kernel);
+        # this is the route hfa_align_batch / decode_batch take on their own
+        rt0 = plan.routing()
+        unsplit = rt0["warp_utts"] == 0 and rt0["cta_utts"] == 0 and \
+            rt0["band_warps"] + rt0["big_band_warps"] == int(len(T))        # hfa_align_batch's own rule
+        fused = os.environ.get("HFA_FUSED", "1" if unsplit else "0") != "0"
+        if fused:
+            try:
+                ops.forward_fused(wss[0], plan.handle, dt)
+                torch.cuda.synchronize()
+            except _lib.HfaError:
+                fused = False
 
         d2h_stream = torch.cuda.Stream()
         d2h_done = [None] * n_sets
@@ -260,10 +272,15 @@ def main():
                 torch.cuda.current_stream().wait_event(d2h_done[k])
             if evs is not None:
                 evs[0].record()
-            ops.emission(ws, plan.handle, dt)
-            if evs is not None:
-                evs[1].record()
-            ops.viterbi_forward(ws, plan.handle, None)
+            if fused:
+                if evs is not None:
+                    evs[1].record()
+                ops.forward_fused(ws, plan.handle, dt)
+            else:
+                ops.emission(ws, plan.handle, dt)
+                if evs is not None:
+                    evs[1].record()
+                ops.viterbi_forward(ws, plan.handle, None)
             if evs is not None:
                 evs[2].record()
             ops.backtrace(ws, plan.handle, res, None, None)
@@ -342,7 +359,10 @@ def main():
                    "h2d_bytes_per_step": int(heads_host[0].numel() * 4),
                    "d2h_bytes_per_step": int(plan.result_bytes), "ms_per_step": 1e3 * e2e_s / steps}
         alg = plan.algorithmic_bytes(dt)
-        return dict(T=T, S=S, V=V, desc=desc, ids_cat=ids_cat, head0=heads_host[0], ms=ms, st_ms=st_ms,
+        if fused:
+            alg = dict(alg, emission=0, dp=plan.algorithmic_bytes_fused(dt))
+        return dict(fused=fused, T=T, S=S, V=V, desc=desc, ids_cat=ids_cat, head0=heads_host[0], ms=ms, st_ms=st_ms,
+                    routing=plan.routing(),
                     cells=cells, frames=frames, clk=clk, launches=launches, e2e=e2e, alg=alg,
                     n_sets=n_sets, bytes_per_set=int(heads_host[0].numel() * 4 + plan.workspace_bytes))
 
@@ -362,12 +382,26 @@ def main():
         tr = None
         if traffic and wl in traffic:
             tr = traffic[wl].get("dp_dram_bytes_per_step")
-        return {"bound": "hbm", "kernel": "hfa_dp_warp_kernel<K> (all state classes of one step, concurrent)",
+        rt = m["routing"]
+        names = []
+        if rt["band_warps"]:
+            names.append(f"hfa_dp_band_kernel<{rt['band_k']}> ({rt['band_warps']} compute warps, several per utterance)")
+        if rt["big_band_warps"]:
+            names.append(f"hfa_dp_band_kernel<{rt['big_band_k']}> ({rt['big_band_warps']} compute warps, S > 256)")
+        if rt["warp_utts"]:
+            names.append(f"hfa_dp_warp_any_kernel ({rt['warp_utts']} utterances, one warp each)")
+        if rt["cta_utts"]:
+            names.append(f"hfa_dp_cta_kernel ({rt['cta_utts']} utterances)")
+        em_ms = float(m["st_ms"][0])
+        return {"bound": "hbm", "kernel": " + ".join(names) + (
+                    " with the emissions computed by its producer warps (fused stages 1+2; + hfa_edge_kernel)"
+                    if m["fused"] else " = the DP forward stage of one step"),
+                "keeps_dp": rt["keeps_dp"], "fused_emission": m["fused"],
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": tr,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": m["alg"]["dp"],
                 "stage_ms": {"emission": float(m["st_ms"][0]), "dp": float(m["st_ms"][1]),
                              "backtrace": float(m["st_ms"][2])},
-                "stage_gbs": {"emission": m["alg"]["emission"] / (m["st_ms"][0] * 1e-3) / 1e9,
+                "stage_gbs": {"emission": (m["alg"]["emission"] / (em_ms * 1e-3) / 1e9) if em_ms > 1e-4 else None,
                               "dp": ach, "backtrace": m["alg"]["backtrace"] / (m["st_ms"][2] * 1e-3) / 1e9}}
 
     m = measure(args.workload, args.steps, args.warmup, do_e2e=True)

@@ -45,6 +45,7 @@ SYMBOLS = {
     "hfa_plan_result_layout": (C.c_int, [_vp, C.POINTER(ResultLayout)]),
     "hfa_plan_algorithmic_bytes": (C.c_int, [_vp, _i32, C.POINTER(_i64 * 3)]),
     "hfa_plan_debug_region": (_i64, [_vp, _i32, C.POINTER(_i64)]),
+    "hfa_plan_routing": (C.c_int, [_vp, C.POINTER(_i32 * 8)]),
     "hfa_plan_upload": (C.c_int, [_vp, _vp, _vp]),
     "hfa_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hfa_emission": (C.c_int, [_vp, _vp, _i32, _vp]),
@@ -52,6 +53,8 @@ SYMBOLS = {
     "hfa_viterbi_forward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "hfa_backtrace": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hfa_align_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "hfa_forward_fused": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hfa_plan_algorithmic_bytes_fused": (_i64, [_vp, _i32]),
     "hfa_debug_unpack_backptr": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
 }
 

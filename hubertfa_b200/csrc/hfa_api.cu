@@ -22,7 +22,7 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
-                               bool keep_dp, float *dp_dump);
+                               bool keep_dp, int64_t fused_row_stride, float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
                                 int64_t max_row_stride, int *n_launched);
 cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype);
@@ -294,13 +294,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             std::sort(lat.begin(), lat.end(), by_len);
         } else if (lat_mode != 0) {
             int64_t nb = 0;
-            bool any_split = false;
             for (int c = 0; c < HFA_NUM_CLASSES; ++c)
-                for (int32_t b : lists[c]) {
-                    nb += n_bands(b, 2);
-                    any_split = any_split || c >= 2;
-                }
-            if (lat_mode == 2 || (any_split && nb <= band_max)) {
+                for (int32_t b : lists[c]) nb += n_bands(b, 2);
+            if (lat_mode == 2 || (nb > 0 && nb <= band_max)) {
                 for (int c = 0; c < HFA_NUM_CLASSES; ++c) {
                     lat_band.insert(lat_band.end(), lists[c].begin(), lists[c].end());
                     lists[c].clear();
@@ -462,16 +458,38 @@ int hfa_plan_algorithmic_bytes(const hfa_plan *p, int32_t dtype, int64_t out[3])
 {
     if (!p || !out) return fail(HFA_ERR_ARG, "hfa_plan_algorithmic_bytes: NULL argument");
     const int64_t in_b = (dtype == HFA_DTYPE_F32) ? 4 : 2;
-    int64_t words = 0;
+    int64_t words = 0, kept_cells = 0, kept_frames = 0;
     for (const HfaUtt &m : p->utt)
-        if (m.status == 0) words += (int64_t)((m.T + 15) / 16) * m.S;
+        if (m.status == 0) {
+            words += (int64_t)((m.T + 15) / 16) * m.S;
+            if (m.dp_off >= 0) {
+                kept_cells += (int64_t)m.T * m.S;
+                kept_frames += m.T;
+            }
+        }
     // unpadded figures: emission reads V logits + 1 edge logit per frame and writes
     // S emissions + {edge_log, not_edge_log, edge_pred}; the DP reads them back and writes 2 bits
     // per cell; the backtrace reads the path's backpointers and operands and writes the segments.
     out[0] = p->total_frames * ((int64_t)p->vocab * in_b + in_b) + p->total_cells * 4 +
              p->total_frames * 12;
-    out[1] = p->total_cells * 4 + p->total_frames * 8 + words * 4;
-    out[2] = p->total_frames * (8 + 8) + p->total_states * 24;
+    // banded routing: the forward pass also writes dp (4 B per cell) and the backtrace reads
+    // dp[t, s_t] instead of the path's emissions and edge logs
+    out[1] = p->total_cells * 4 + p->total_frames * 8 + words * 4 + kept_cells * 4;
+    out[2] = (p->total_frames - kept_frames) * (8 + 8) + kept_frames * (8 + 4) + p->total_states * 24;
+    return HFA_OK;
+}
+
+int hfa_plan_routing(const hfa_plan *p, int32_t out[8])
+{
+    if (!p || !out) return fail(HFA_ERR_ARG, "hfa_plan_routing: NULL argument");
+    out[0] = p->warp_all_count;
+    out[1] = p->band_count[0];
+    out[2] = p->band_k[0];
+    out[3] = p->band_count[1];
+    out[4] = p->band_k[1];
+    out[5] = p->lat_count + p->class_count[HFA_NUM_CLASSES];
+    out[6] = p->dp_store_elems > 0;
+    out[7] = 0;
     return HFA_OK;
 }
 
@@ -605,7 +623,10 @@ static int dp_mode()
     return mode;
 }
 
-int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void *stream)
+// fused_row_stride > 0 (hfa_align_batch only): every utterance is in the banded kernel and the
+// producer warps compute the emissions from the logits themselves
+static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_dump, void *stream,
+                                int64_t fused_row_stride)
 {
     if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_viterbi_forward: NULL plan/workspace");
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
@@ -652,10 +673,10 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k == -3)
             e = hfa_launch_dp_band(c, p->band_k[0], p->band_begin[0], p->band_count[0], c.ws.band_ticket,
-                                   p->dp_store_elems > 0, dp_dump);
+                                   p->dp_store_elems > 0, fused_row_stride, dp_dump);
         else if (items[it].k == -4)
             e = hfa_launch_dp_band(c, p->band_k[1], p->band_begin[1], p->band_count[1],
-                                   c.ws.band_ticket + 1, p->dp_store_elems > 0, dp_dump);
+                                   c.ws.band_ticket + 1, p->dp_store_elems > 0, fused_row_stride, dp_dump);
         else if (items[it].k == -2)
             e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else
@@ -669,6 +690,11 @@ int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void
         }
     }
     return HFA_OK;
+}
+
+int hfa_viterbi_forward(const hfa_plan *p, void *workspace, float *dp_dump, void *stream)
+{
+    return viterbi_forward_impl(p, workspace, dp_dump, stream, 0);
 }
 
 int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame_conf,
@@ -685,12 +711,62 @@ int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame
     return HFA_OK;
 }
 
+static bool fused_ok(const hfa_plan *p, int32_t dtype)
+{
+    const bool all_banded = p->warp_all_count == 0 && p->lat_count == 0 &&
+                            p->class_count[HFA_NUM_CLASSES] == 0 && !p->band_items.empty();
+    return all_banded && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && p->max_row_stride > 0 &&
+           p->vocab <= 256 && p->max_row_stride * 4 * HFA_TILE_T <= 48 * 1024;
+}
+
+int hfa_forward_fused(const hfa_plan *p, void *workspace, int32_t dtype, void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_forward_fused: NULL plan/workspace");
+    if (!fused_ok(p, dtype))
+        return fail(HFA_ERR_UNSUPPORTED, "hfa_forward_fused: needs an all-banded plan that keeps dp, f32 logits "
+                                         "with contiguous rows (set by hfa_set_inputs) and V <= 256");
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    cudaError_t e = hfa_launch_edge(c, p->row_blocks[p->n_utt], dtype);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_forward_fused: edge kernel");
+    g_launches += 1;
+    return viterbi_forward_impl(p, workspace, nullptr, stream, p->max_row_stride);
+}
+
+int64_t hfa_plan_algorithmic_bytes_fused(const hfa_plan *p, int32_t dtype)
+{
+    if (!p) return 0;
+    const int64_t in_b = (dtype == HFA_DTYPE_F32) ? 4 : 2;
+    int64_t words = 0;
+    for (const HfaUtt &m : p->utt)
+        if (m.status == 0) words += (int64_t)((m.T + 15) / 16) * m.S;
+    return p->total_frames * ((int64_t)p->vocab * in_b + in_b) + p->total_frames * 12 + words * 4 +
+           p->total_cells * 4;
+}
+
 int hfa_align_batch(const hfa_plan *p, void *workspace, int32_t dtype, void *result,
                     float *frame_conf, void *stream)
 {
-    int rc = hfa_emission(p, workspace, dtype, stream);
-    if (rc != HFA_OK) return rc;
-    rc = hfa_viterbi_forward(p, workspace, nullptr, stream);
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_align_batch: NULL plan/workspace");
+    // Fused route (small batches): when every utterance is in the banded kernel, keeps its dp, and
+    // the logits are f32 rows the TMA engine can fetch, the emission stage disappears -- only the
+    // edge stream is computed up front, the emissions are produced inside the DP kernel's producer
+    // warps and never written to HBM.  HFA_FUSED=0 keeps the three-stage route.
+    // Measured (B200): the fused route wins when no utterance is split into several bands (config 1:
+    // 0.137 vs 0.173 ms per decode) and loses otherwise -- every band of an utterance recomputes the
+    // softmax normaliser of its frames, and a single producer warp then cannot keep up with its
+    // compute warp (config 2: 0.29 vs 0.22 ms).  HFA_FUSED=0 / 1 forces the choice.
+    static const int fused_mode = [] { const char *v = std::getenv("HFA_FUSED"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
+    int64_t n_valid = 0;
+    for (const HfaUtt &m : p->utt) n_valid += (m.status == 0);
+    const bool unsplit = (int64_t)p->band_items.size() == n_valid;
+    int rc;
+    if ((fused_mode == 1 || (fused_mode == -1 && unsplit)) && fused_ok(p, dtype)) {
+        rc = hfa_forward_fused(p, workspace, dtype, stream);
+    } else {
+        rc = hfa_emission(p, workspace, dtype, stream);
+        if (rc != HFA_OK) return rc;
+        rc = viterbi_forward_impl(p, workspace, nullptr, stream, 0);
+    }
     if (rc != HFA_OK) return rc;
     return hfa_backtrace(p, workspace, result, frame_conf, nullptr, stream);
 }

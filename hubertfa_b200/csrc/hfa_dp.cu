@@ -792,10 +792,14 @@ template <int K> constexpr size_t hfa_band_smem_bytes()
            (size_t)(HFA_BAND_STAGES * HFA_TILE_T + 2) * sizeof(float2) +
            (size_t)HFA_BAND_STAGES * 32 * 16 + 2 * HFA_BAND_STAGES * sizeof(uint64_t) + 16;
 }
+// fused emission: [keep mask 8 u32][kept ids 256 i32][16 x {max, lse}][2 mbarriers][2 shifts + pad]
+// [2 logits stages of lstage_bytes]
+constexpr size_t HFA_FUSED_FIXED_BYTES = 8 * 4 + 256 * 4 + 16 * 8 + 2 * 8 + 16;
 
-template <int K, bool DUMP, bool KEEP>
+template <int K, bool DUMP, bool KEEP, bool FUSED>
 __global__ void __launch_bounds__(64)
-hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump)
+hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump, int V,
+                   int lstage_bytes)
 {
     static_assert(32 % K == 0 && K >= 2, "the halo (32 states) must be a whole number of lanes");
     constexpr int TT = HFA_TILE_T, NST = HFA_BAND_STAGES;
@@ -846,6 +850,70 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         const uint32_t row_b = (uint32_t)cols * 4u;
         const float *g_emis = ws.emis + m.emis_off + c0;
         const float2 *g_edge = ws.edge2 + m.edge_off;
+        // ---- fused emission (FUSED): the producer computes the emission window itself.  The
+        // logits rows of a tile arrive by ONE bulk copy ([16][row stride] f32, contiguous in the
+        // [T, V+2] head output) into a double-buffered logits stage; the masked log-softmax and
+        // the gather by phoneme id follow hfa_emission_stream_kernel instruction for instruction
+        // (4 lanes per frame over the kept ids, xor-shuffle combine, (x - max) - lse), so a fused
+        // and an unfused run produce the same bits.  No emission ever touches HBM.
+        uint32_t *mask_sm = reinterpret_cast<uint32_t *>(slot + 4);
+        int32_t *kept_sm = reinterpret_cast<int32_t *>(mask_sm + 8);
+        float2 *stat_sm = reinterpret_cast<float2 *>(kept_sm + 256);
+        uint64_t *lbar = reinterpret_cast<uint64_t *>(stat_sm + 16);
+        int32_t *shift_sm = reinterpret_cast<int32_t *>(lbar + 2);
+        unsigned char *lstage0 = reinterpret_cast<unsigned char *>(shift_sm + 4);
+        int n_kept = 0, row_st = 0;
+        uint32_t gid[K];
+        int kreg[16];
+        const unsigned char *g_logits = nullptr;
+        auto issue_logits = [&](int i) {                       // lane 0 only
+            const int ls = i & 1;
+            const int t0 = i * TT;
+            const int rows = min(TT, T - t0);
+            const unsigned char *src = g_logits + (int64_t)t0 * row_st * 4;
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+            const uint32_t bytes = (shift + (uint32_t)(((int64_t)(rows - 1) * row_st + V) * 4) + 15u) & ~15u;
+            shift_sm[ls] = (int32_t)shift;
+            hfa_mbar_expect_tx(&lbar[ls], bytes);
+            hfa_bulk_load(lstage0 + (size_t)ls * lstage_bytes, src - shift, bytes, &lbar[ls]);
+        };
+        if constexpr (FUSED) {
+            const HfaInput in = ws.inputs[u];
+            g_logits = reinterpret_cast<const unsigned char *>(in.frame);
+            row_st = (int)in.frame_st;
+            const int32_t *ids = ws.ids + m.seg_off;
+            if (lane < 8) mask_sm[lane] = (lane == 0) ? 1u : 0u;             // id 0 always kept (:39)
+            if (lane == 0) {
+                hfa_mbar_init(&lbar[0], 1);
+                hfa_mbar_init(&lbar[1], 1);
+                hfa_fence_mbar_init();
+            }
+            __syncwarp();
+            for (int q = lane; q < S; q += 32) atomicOr(&mask_sm[ids[q] >> 5], 1u << (ids[q] & 31));
+            __syncwarp();
+            const int mask_words = (V + 31) >> 5;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) n_kept += (w < mask_words) ? __popc(mask_sm[w]) : 0;
+            for (int v = lane; v < V; v += 32) {
+                if ((mask_sm[v >> 5] >> (v & 31)) & 1u) {
+                    int pos = __popc(mask_sm[v >> 5] & ((1u << (v & 31)) - 1u));
+                    for (int w = 0; w < (v >> 5); ++w) pos += __popc(mask_sm[w]);
+                    kept_sm[pos] = v;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int sgl = c0 + lane * K + k;
+                gid[k] = (sgl < S) ? (uint32_t)ids[sgl] : (uint32_t)V;       // pad columns: -inf
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = (lane & 3) + 4 * j;
+                kreg[j] = (k < n_kept && k < 256) ? kept_sm[k] : 0;
+            }
+            if (lane == 0) issue_logits(0);
+        }
         uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + 2 * lane;
         // dp store: the compute warp leaves dp[t][.] of a tile in the stage it has just consumed (in
         // place of the emissions); before the stage is refilled its owned columns go out as one
@@ -869,14 +937,93 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
             if (i >= n_tiles) continue;
             const int t0 = i * TT;
             const int rows = min(TT, T - t0);
-            if (lane == 0) {
-                hfa_mbar_expect_tx(&full[st], (uint32_t)rows * row_b + TT * (uint32_t)sizeof(float2));
-                hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &full[st]);
+            if constexpr (FUSED) {
+                if (lane == 0) {
+                    hfa_mbar_expect_tx(&full[st], TT * (uint32_t)sizeof(float2));
+                    hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &full[st]);
+                    if (i + 1 < n_tiles) issue_logits(i + 1);     // its stage was read during tile i-1
+                }
+                const int ls = i & 1;
+                hfa_mbar_wait(&lbar[ls], (uint32_t)((i >> 1) & 1));
+                const float *xs = reinterpret_cast<const float *>(lstage0 + (size_t)ls * lstage_bytes + shift_sm[ls]);
+                // normaliser: lane -> (row = 8 * pass + lane / 4, part = lane % 4), kept ids only.
+                // The lane's kept ids sit in registers (kreg, <= 16 of them: up to 64 kept ids) so
+                // that its loads go out back to back; the max / sum chains keep the standalone
+                // kernel's order (k = part, part + 4, ...).
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int rr = 8 * pass + (lane >> 2);
+                    const float *row = xs + rr * row_st;
+                    const int part = lane & 3;
+                    float mx = HFA_NEG_INF, sum = 0.0f;
+                    if (n_kept <= 64) {                                       // warp-uniform
+                        float xv[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xv[j] = (part + 4 * j < n_kept) ? row[kreg[j]] : HFA_NEG_INF;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, xv[j]);
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xv[j] = expf(__fsub_rn(xv[j], mx));
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (part + 4 * j < n_kept) sum = __fadd_rn(sum, xv[j]);
+                    } else {
+                        for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, row[kept_sm[k]]);
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                        for (int k = part; k < n_kept; k += 4)
+                            sum = __fadd_rn(sum, expf(__fsub_rn(row[kept_sm[k]], mx)));
+                    }
+                    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+                    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+                    if (part == 0) stat_sm[rr] = make_float2(mx, logf(sum));
+                }
+                __syncwarp();
+                // gather by phoneme id: K window columns per lane, the layout the compute warp reads;
+                // four rows at a time so that their loads overlap
+                float *dst = tile0 + st * TILE_FLOATS + lane * K;
+                auto put_row = [&](int r, const float (&o)[K]) {
+                    if constexpr (K % 4 == 0) {
+#pragma unroll
+                        for (int q = 0; q < K / 4; ++q)
+                            reinterpret_cast<float4 *>(dst + r * W)[q] =
+                                make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < K / 2; ++q)
+                            reinterpret_cast<float2 *>(dst + r * W)[q] = make_float2(o[2 * q], o[2 * q + 1]);
+                    }
+                };
+                for (int r0 = 0; r0 < rows; r0 += 4) {
+                    float o[4][K];
+                    float2 sv[4];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int r = min(r0 + d, TT - 1);
+                        sv[d] = stat_sm[r];
+                        const float *row = xs + r * row_st;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) o[d][k] = (gid[k] < (uint32_t)V) ? row[gid[k]] : HFA_NEG_INF;
+                    }
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) o[d][k] = __fsub_rn(__fsub_rn(o[d][k], sv[d].x), sv[d].y);
+                        if (r0 + d < rows) put_row(r0 + d, o[d]);
+                    }
+                }
+            } else {
+                if (lane == 0) {
+                    hfa_mbar_expect_tx(&full[st], (uint32_t)rows * row_b + TT * (uint32_t)sizeof(float2));
+                    hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &full[st]);
+                }
+                __syncwarp();
+                if (lane < rows)
+                    hfa_bulk_load(tile0 + st * TILE_FLOATS + lane * W, g_emis + (int64_t)(t0 + lane) * Sp, row_b,
+                                  &full[st]);
             }
-            __syncwarp();
-            if (lane < rows)
-                hfa_bulk_load(tile0 + st * TILE_FLOATS + lane * W, g_emis + (int64_t)(t0 + lane) * Sp, row_b,
-                              &full[st]);
             if (has_left && i > 0) {
                 // the window's first 32 states at the start of tile i = the left band's last 32
                 // after its tile i-1: lane j relays state j
@@ -1183,30 +1330,41 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
 }
 
 // banded kernel: items [item_begin, item_begin + n_items) of the plan's band table, one CTA each
-template <int K, bool DUMP, bool KEEP>
+template <int K, bool DUMP, bool KEEP, bool FUSED>
 static cudaError_t launch_band(const HfaLaunchCtx &c, int item_begin, int n_items, int32_t *ticket,
-                               float *dp_dump)
+                               float *dp_dump, int64_t row_stride)
 {
-    const size_t smem = hfa_band_smem_bytes<K>();
-    cudaError_t e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, DUMP, KEEP>,
+    size_t smem = hfa_band_smem_bytes<K>();
+    int lstage = 0;
+    if (FUSED) {
+        lstage = (int)(((int64_t)HFA_TILE_T * row_stride * 4 + 32 + 15) & ~(int64_t)15);
+        smem = ((smem + 15) & ~(size_t)15) + HFA_FUSED_FIXED_BYTES + 2 * (size_t)lstage;
+    }
+    cudaError_t e = cudaFuncSetAttribute(hfa_dp_band_kernel<K, DUMP, KEEP, FUSED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hfa_dp_band_kernel<K, DUMP, KEEP><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump);
+    hfa_dp_band_kernel<K, DUMP, KEEP, FUSED><<<n_items, 64, smem, c.stream>>>(c.ws, item_begin, ticket, dp_dump,
+                                                                            c.vocab, lstage);
     return cudaGetLastError();
 }
 
-// keep_dp: the plan reserved a dp store for the utterances of this list (all or none)
+// keep_dp: the plan reserved a dp store for the utterances of this list (all or none).
+// fused_row_stride > 0: compute the emissions inside the kernel from f32 logits whose rows are
+// contiguous with at most this stride (requires keep_dp: nothing else holds what the backtrace needs)
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
-                               bool keep_dp, float *dp_dump)
+                               bool keep_dp, int64_t fused_row_stride, float *dp_dump)
 {
     if (n_items <= 0) return cudaSuccess;
-#define HFA_BAND_CASE(KK)                                                                           \
-    case KK:                                                                                        \
-        if (dp_dump != nullptr)                                                                     \
-            return keep_dp ? launch_band<KK, true, true>(c, item_begin, n_items, ticket, dp_dump)   \
-                           : launch_band<KK, true, false>(c, item_begin, n_items, ticket, dp_dump); \
-        return keep_dp ? launch_band<KK, false, true>(c, item_begin, n_items, ticket, dp_dump)      \
-                       : launch_band<KK, false, false>(c, item_begin, n_items, ticket, dp_dump)
+    const bool fused = fused_row_stride > 0 && keep_dp && dp_dump == nullptr;
+#define HFA_BAND_CASE(KK)                                                                              \
+    case KK:                                                                                           \
+        if (fused) return launch_band<KK, false, true, true>(c, item_begin, n_items, ticket, nullptr,  \
+                                                             fused_row_stride);                        \
+        if (dp_dump != nullptr)                                                                        \
+            return keep_dp ? launch_band<KK, true, true, false>(c, item_begin, n_items, ticket, dp_dump, 0)   \
+                           : launch_band<KK, true, false, false>(c, item_begin, n_items, ticket, dp_dump, 0); \
+        return keep_dp ? launch_band<KK, false, true, false>(c, item_begin, n_items, ticket, dp_dump, 0)      \
+                       : launch_band<KK, false, false, false>(c, item_begin, n_items, ticket, dp_dump, 0)
     switch (k) {
         HFA_BAND_CASE(2);
         HFA_BAND_CASE(4);

@@ -66,6 +66,16 @@ class AlignPlan:
             raise HfaError("plan already destroyed")
         return int(self._h.value)
 
+    def routing(self) -> dict:
+        """Which forward-pass kernels the plan chose for this batch (hfa_plan_routing)."""
+        out = (C.c_int32 * 8)()
+        check(self._lib.hfa_plan_routing(self._h, C.byref(out)))
+        return dict(warp_utts=out[0], band_warps=out[1], band_k=out[2], big_band_warps=out[3],
+                    big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]))
+
+    def algorithmic_bytes_fused(self, dtype: int = _lib.DTYPE_F32) -> int:
+        return int(self._lib.hfa_plan_algorithmic_bytes_fused(self._h, dtype))
+
     def algorithmic_bytes(self, dtype: int = _lib.DTYPE_F32):
         out = (C.c_int64 * 3)()
         check(self._lib.hfa_plan_algorithmic_bytes(self._h, dtype, C.byref(out)))
@@ -180,6 +190,14 @@ def align_batch(workspace: torch.Tensor, plan: int, dtype: int, result: torch.Te
     with torch.cuda.device(workspace.device):
         check(_lib.load().hfa_align_batch(plan, workspace.data_ptr(), dtype, result.data_ptr(),
                                           _ptr(frame_conf), _stream_ptr()), "hfa_align_batch")
+
+
+@torch.library.custom_op("hfa::forward_fused", mutates_args=("workspace",), device_types="cuda")
+def forward_fused(workspace: torch.Tensor, plan: int, dtype: int) -> None:
+    """Edge stream + banded DP with the emissions computed inside the kernel (small batches only;
+    raises HfaError when the plan / inputs do not qualify)."""
+    with torch.cuda.device(workspace.device):
+        check(_lib.load().hfa_forward_fused(plan, workspace.data_ptr(), dtype, _stream_ptr()), "hfa_forward_fused")
 
 
 def unpack_backptr(plan: AlignPlan, workspace: torch.Tensor, utt: int) -> torch.Tensor:

@@ -92,7 +92,15 @@ int hfa_plan_result_layout(const hfa_plan *plan, HfaResultLayout *out);
  * [1] DP forward, [2] backtrace+finalize */
 int hfa_plan_algorithmic_bytes(const hfa_plan *plan, int32_t dtype, int64_t out[3]);
 
-/* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace.
+/* Which forward-pass kernels this plan uses (filled at hfa_plan_create from the batch shape):
+ * out[0] utterances in the one-warp-per-utterance kernel, out[1] warps (bands) and out[2] states per
+ * lane of the banded kernel for S <= 256 (small batches: several warps per utterance), out[3] / out[4]
+ * the same for S > 256, out[5] utterances in the CTA-per-utterance kernels, out[6] 1 if the banded
+ * forward pass keeps dp for the backtrace, out[7] reserved. */
+int hfa_plan_routing(const hfa_plan *plan, int32_t out[8]);
+
+/* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace and
+ * zeroes the banded kernel's exchange table.
  * Must be enqueued once per (plan, workspace) before any compute call. */
 int hfa_plan_upload(const hfa_plan *plan, void *workspace /*[dev]*/, void *stream);
 
@@ -133,6 +141,17 @@ int hfa_backtrace(const hfa_plan *plan, void *workspace, void *result, float *fr
 /* = hfa_emission + hfa_viterbi_forward + hfa_backtrace on the inputs of the last hfa_set_inputs. */
 int hfa_align_batch(const hfa_plan *plan, void *workspace, int32_t dtype, void *result,
                     float *frame_conf, void *stream);
+
+/* ---- the fused forward pass (small batches) -------------------------------------------------- */
+/* Stages 1+2 in one go for plans whose utterances are all in the banded kernel (hfa_plan_routing:
+ * out[0] == out[5] == 0, out[6] == 1), f32 logits with contiguous rows and V <= 256: the edge stream
+ * is computed up front, the emissions (alignment_decoder.py:53-65,239) are produced inside the DP
+ * kernel by its producer warps and never written to HBM.  hfa_align_batch takes this route on its
+ * own when it applies; this entry point exists so that the route can be timed and tested by stage.
+ * Returns HFA_ERR_UNSUPPORTED when the plan / inputs do not qualify.  Follow with hfa_backtrace. */
+int hfa_forward_fused(const hfa_plan *plan, void *workspace, int32_t dtype, void *stream);
+/* algorithmic HBM bytes of that pass: logits + edge logits in, edge logs + backpointers + dp out */
+int64_t hfa_plan_algorithmic_bytes_fused(const hfa_plan *plan, int32_t dtype);
 
 /* ---- introspection for tests: unpacked backpointers of one utterance ------------------------ */
 /* out: [dev] int8 [T_b][S_b], codes 0/1/2 (row 0 is -1 like the reference, :247). */

@@ -276,3 +276,63 @@ def test_host_pipeline_matches_decode_batch():
                 ridx, rtim, riv = ref.segments(b)
                 assert np.array_equal(idx, ridx) and np.array_equal(tim, rtim) and np.array_equal(iv, riv)
                 assert bits(out["total_conf"][b]) == bits(ref.total_confidence[b])
+
+
+def test_fused_forward_equals_three_stage_route():
+    """Small batches: hfa_forward_fused (emissions computed by the DP kernel's producer warps, never
+    written to HBM) must give the same bits as hfa_emission + hfa_viterbi_forward -- backpointers,
+    kept dp, results -- for strided [T, V+2] head views, all band widths, S up to 1030."""
+    import torch
+    from hubertfa_b200 import _lib, ops, synth
+    V = 63
+    T = np.array([500, 130, 257, 700, 16, 17, 1, 333, 900, 1300], dtype=np.int32)
+    S = np.array([40, 7, 65, 150, 5, 33, 3, 97, 256, 1030], dtype=np.int32)
+    vocab, items = synth.make_batch(T, S, V, seed=4242, style="dictionary", planted=True)
+    dev = torch.device("cuda")
+    ids = np.concatenate([it["ids"] for it in items]).astype(np.int32)
+    heads = []
+    for it in items:                                  # the network head layout: col 0 edge, 2.. frame
+        h = torch.zeros(it["frame"].shape[1], V + 2)
+        h[:, 0] = it["edge"][0]
+        h[:, 2:] = it["frame"][0]
+        heads.append(h.to(dev))
+    outs = []
+    for fused in (False, True):
+        plan = ops.AlignPlan(T, S, ids, V, 0.02)
+        rt = plan.routing()
+        assert rt["warp_utts"] == 0 and rt["cta_utts"] == 0 and rt["keeps_dp"]
+        ws, res = plan.new_workspace(dev), plan.new_result(dev)
+        plan.upload(ws)
+        plan.set_inputs(ws, [h[:, 2:].data_ptr() for h in heads], [V + 2] * len(heads), [1] * len(heads),
+                        [h[:, 0].data_ptr() for h in heads], [V + 2] * len(heads))
+        if fused:
+            ops.forward_fused(ws, plan.handle, _lib.DTYPE_F32)
+        else:
+            ops.emission(ws, plan.handle, _lib.DTYPE_F32)
+            ops.viterbi_forward(ws, plan.handle, None)
+        fc = torch.empty(plan.total_frames, dtype=torch.float32, device=dev)
+        dpp = torch.empty(plan.total_frames, dtype=torch.float32, device=dev)
+        ops.backtrace(ws, plan.handle, res, fc, dpp)
+        torch.cuda.synchronize()
+        outs.append((plan.debug_region(ws, "bp").cpu().numpy().copy(), res.cpu().numpy().copy(),
+                     fc.cpu().numpy(), dpp.cpu().numpy()))
+    for j in (0, 2, 3):                               # backpointer words, frame confidence, dp on the path
+        assert np.array_equal(outs[0][j].view(np.uint8), outs[1][j].view(np.uint8))
+    va, vb = plan.views(outs[0][1]), plan.views(outs[1][1])
+    for key in ("status", "n_seg", "end_state", "final_score", "total_conf"):
+        assert np.array_equal(va[key].view(np.uint8), vb[key].view(np.uint8)), key
+    for b in range(plan.n_utt):                       # segment slots beyond n_seg are never written
+        o, k = int(plan.seg_off[b]), int(va["n_seg"][b])
+        for key in ("ph_idx_seq", "ph_time_int", "intervals"):
+            assert np.array_equal(va[key][o:o + k], vb[key][o:o + k]), (b, key)
+    # and decode_batch (hfa_align_batch picks the fused route on its own) agrees with it
+    from hubertfa_b200.alignment_decoder import AlignmentDecoder
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    r = dec.decode_batch([h[None, :, 2:] for h in heads], [h[None, :, 0] for h in heads],
+                         [it["ph_seq"] for it in items])
+    v = ops.AlignPlan(T, S, ids, V, synth.MELSPEC_50FPS["hop_length"] / synth.MELSPEC_50FPS["sample_rate"]).views(outs[1][1])
+    assert np.array_equal(r.n_seg, v["n_seg"])
+    for b in range(len(items)):
+        idx, tim, _ = r.segments(b)
+        o, k = int(r.seg_off[b]), int(v["n_seg"][b])
+        assert np.array_equal(idx, v["ph_idx_seq"][o:o + k]) and np.array_equal(tim, v["ph_time_int"][o:o + k])

@@ -41,7 +41,11 @@ def test_plan_layout_and_statuses():
             L.intervals]
     assert offs == sorted(offs) and all(o % 16 == 0 for o in offs) and L.total_bytes >= offs[-1] + 16 * 348
     alg = p.algorithmic_bytes()
-    assert alg["dp"] == p.total_cells * 4 + p.total_frames * 8 + 4 * (32 * 40 + 2 * 300)
+    # a batch this small goes to the banded kernel, whose forward pass also keeps dp (4 B per cell)
+    assert p.routing()["keeps_dp"] and p.routing()["warp_utts"] == 0 and p.routing()["cta_utts"] == 0
+    assert alg["dp"] == p.total_cells * 4 + p.total_frames * 8 + 4 * (32 * 40 + 2 * 300) + p.total_cells * 4
+    assert p.algorithmic_bytes_fused() == p.total_frames * (63 * 4 + 4 + 12) + 4 * (32 * 40 + 2 * 300) \
+        + p.total_cells * 4
     assert alg["emission"] == p.total_frames * (63 * 4 + 4) + p.total_cells * 4 + p.total_frames * 12
     p.close()
     with pytest.raises(Exception):
