@@ -32,6 +32,9 @@ cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const f
 cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
                                  const HfaResultPtrs &res, float *frame_conf, float *dp_path);
 cudaError_t hfa_launch_unpack_bp(const HfaLaunchCtx &c, int utt, int8_t *out);
+cudaError_t hfa_launch_jump_tables(const HfaLaunchCtx &c, int n_blocks);
+cudaError_t hfa_launch_backtrace_tables(const HfaLaunchCtx &c, const int32_t *order, int n,
+                                        const HfaResultPtrs &res, float *frame_conf, float *dp_path);
 
 namespace {
 
@@ -103,6 +106,8 @@ struct hfa_plan {
     std::vector<HfaBandItem> band_items;
     int32_t band_begin[2] = {0, 0}, band_count[2] = {0, 0}, band_k[2] = {2, 4};
     int64_t band_xchg_elems = 0, dp_store_elems = 0;
+    std::vector<int32_t> jblk_utt, jblk_first; // jump-table kernel: 256-word blocks per utterance
+    int32_t n_valid = 0, n_kept = 0;           // valid utterances / utterances that keep dp
     int32_t bt_begin = 0;
     std::vector<int32_t> row_blocks;           // [n+1]
     std::vector<int32_t> block_utt;            // [row_blocks[n]]
@@ -111,7 +116,7 @@ struct hfa_plan {
     // byte offsets
     int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
-            o_last = 0, o_dpst = 0, o_band_items = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
+            o_last = 0, o_dpst = 0, o_jump = 0, o_moves = 0, o_rowent = 0, o_band_items = 0, o_jblk_utt = 0, o_jblk_first = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
     std::vector<unsigned char> head;           // host image of the head (without inputs)
     // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
     // aligned base pointers and positive row strides of at most this many elements (TMA path)
@@ -140,6 +145,11 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.rev_t = reinterpret_cast<int32_t *>(b + p->o_revt);
     w.dp_last = reinterpret_cast<float *>(b + p->o_last);
     w.dp_store = reinterpret_cast<float *>(b + p->o_dpst);
+    w.jump = reinterpret_cast<uint8_t *>(b + p->o_jump);
+    w.moves = reinterpret_cast<uint8_t *>(b + p->o_moves);
+    w.row_entry = reinterpret_cast<int32_t *>(b + p->o_rowent);
+    w.jblk_utt = reinterpret_cast<const int32_t *>(b + p->o_jblk_utt);
+    w.jblk_first = reinterpret_cast<const int32_t *>(b + p->o_jblk_first);
     w.band_items = reinterpret_cast<const HfaBandItem *>(b + p->o_band_items);
     w.band_ticket = reinterpret_cast<int32_t *>(b + p->o_band_ticket);
     w.band_xchg = reinterpret_cast<uint4 *>(b + p->o_band_xchg);
@@ -355,6 +365,17 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         };
         add_bands(lat_band, 0);
         add_bands(big_band, 1);
+        // jump-table kernel (backtrace of the utterances that keep dp): one thread per backpointer word
+        p->n_valid = (int32_t)all.size();
+        for (const HfaUtt &m : p->utt) p->n_kept += (m.status == 0 && m.dp_off >= 0);
+        p->jblk_first.assign((size_t)n_utt + 1, 0);
+        for (int32_t b = 0; b < n_utt; ++b) {
+            const HfaUtt &m = p->utt[b];
+            const int64_t w = (m.status == 0 && m.dp_off >= 0) ? (int64_t)((m.T + 15) / 16) * m.Sp : 0;
+            const int32_t nblk = (int32_t)((w + 255) / 256);
+            p->jblk_first[b + 1] = p->jblk_first[b] + nblk;
+            p->jblk_utt.insert(p->jblk_utt.end(), (size_t)nblk, b);
+        }
         // merged warp-kernel list: longest expected run time first (frames x per-frame cost, which
         // grows with the states per lane)
         std::vector<int32_t> warp_all;
@@ -388,6 +409,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             p->block_utt.insert(p->block_utt.end(), (size_t)(p->row_blocks[b + 1] - p->row_blocks[b]), b);
         p->o_blkutt = region((int64_t)p->block_utt.size() * 4);
         p->o_band_items = region((int64_t)p->band_items.size() * sizeof(HfaBandItem));
+        p->o_jblk_utt = region((int64_t)p->jblk_utt.size() * 4);
+        p->o_jblk_first = region((int64_t)p->jblk_first.size() * 4);
         p->head_bytes = o;
         p->o_inputs = region((int64_t)n_utt * sizeof(HfaInput));
         p->o_emis = region(emis * 4);
@@ -399,6 +422,11 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_revt = region(p->total_states * 4);
         p->o_last = region((int64_t)n_utt * 8);
         p->o_dpst = region(p->dp_store_elems * 4);
+        const bool jump_tables = p->dp_store_elems > 0;      // latency plans: parallel backtrace
+        p->o_jump = region(jump_tables ? words : 0);
+        p->o_moves = region(jump_tables ? words : 0);
+        p->o_rowent = region(jump_tables ? edge / 16 * 4 : 0);
+
         p->o_band_ticket = region(p->band_items.empty() ? 0 : 8);
         p->o_band_xchg = region(p->band_xchg_elems * 16);
         p->band_bytes = o - p->o_band_ticket;
@@ -414,6 +442,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         if (!p->band_items.empty())
             std::memcpy(p->head.data() + p->o_band_items, p->band_items.data(),
                         p->band_items.size() * sizeof(HfaBandItem));
+        if (!p->jblk_utt.empty())
+            std::memcpy(p->head.data() + p->o_jblk_utt, p->jblk_utt.data(), p->jblk_utt.size() * 4);
+        std::memcpy(p->head.data() + p->o_jblk_first, p->jblk_first.data(), p->jblk_first.size() * 4);
         std::memcpy(p->head.data() + p->o_rowblk, p->row_blocks.data(), (size_t)(n_utt + 1) * 4);
         if (!p->block_utt.empty())
             std::memcpy(p->head.data() + p->o_blkutt, p->block_utt.data(), p->block_utt.size() * 4);
@@ -704,6 +735,16 @@ int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame
     if (p->n_utt == 0) return HFA_OK;
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
     const HfaResultPtrs r = make_res(p, result);
+    if (!p->jblk_utt.empty()) {
+        // utterances whose forward pass kept dp (latency plans): jump tables (parallel), then one CTA
+        // per utterance; the warp-per-utterance kernel below skips them (and they skip the others)
+        cudaError_t ej = hfa_launch_jump_tables(c, (int)p->jblk_utt.size());
+        if (ej == cudaSuccess)
+            ej = hfa_launch_backtrace_tables(c, c.ws.order + p->bt_begin, p->n_valid, r, frame_conf, dp_path);
+        if (ej != cudaSuccess) return cuda_fail(ej, "hfa_backtrace: table kernels");
+        g_launches += 2;
+        if (p->n_kept == p->n_utt) return HFA_OK;           // nothing left for the warp kernel
+    }
     cudaError_t e = hfa_launch_backtrace(c, c.ws.order + p->bt_begin, p->n_utt, r, frame_conf,
                                          dp_path);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_backtrace: launch");

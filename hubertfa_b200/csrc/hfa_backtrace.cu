@@ -29,6 +29,54 @@ __device__ __forceinline__ double seg_time(const float *p, int t, int T, double 
     return __dmul_rn(frame_length, __dadd_rn((double)(float)t, d));   // :105-108
 }
 
+// One 16-frame row of the backward walk, entered at state `cur` in its last frame `tt`.
+// word(s) = backpointer word of state s in this row; bit f = "advanced by one at frame f", bit 16+f =
+// "jumped over an SP".  The walk hops from move to move (clz); on_move(state, f) is called for every
+// move met (latest first), on_span(state, f_lo, f_hi) for every run of frames spent in one state.
+// Row 0 ends with the segment that frame 0 always opens (:277).  Returns the state the path has
+// before the row's first frame.
+template <typename FMove, typename FSpan>
+__device__ __forceinline__ int hfa_walk_row(const uint32_t *__restrict__ row_words, int cur, int tt, bool row0,
+                                            FMove on_move, FSpan on_span)
+{
+    while (tt >= 0) {
+        const uint32_t wc = row_words[cur];
+        uint32_t nz = (wc | (wc >> 16)) & 0xffffu & ((2u << tt) - 1u);
+        if (row0) nz |= 1u;
+        if (nz == 0u) {
+            on_span(cur, 0, tt);
+            break;
+        }
+        const int tp = 31 - __clz(nz);
+        on_span(cur, tp, tt);
+        on_move(cur, tp);
+        if (row0 && tp == 0) break;
+        cur -= ((wc >> (16 + tp)) & 1u) ? 2 : 1;
+        tt = tp - 1;
+    }
+    return cur;
+}
+
+// Jump tables (latency plans): for every row w and every state s, where does a path that is in s at
+// the row's last frame come from, and how many segments does it open on the way?  One thread per
+// backpointer word; the serial part of the backtrace then takes ONE table lookup per 16 frames.
+__global__ void __launch_bounds__(256)
+hfa_jump_table_kernel(HfaWs ws)
+{
+    const int u = ws.jblk_utt[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    const int n_rows = (m.T + 15) >> 4;
+    const int64_t idx = (int64_t)(blockIdx.x - ws.jblk_first[u]) * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_rows * m.Sp) return;
+    const int w = (int)(idx / m.Sp), s = (int)(idx - (int64_t)w * m.Sp);
+    const int tt = (w == n_rows - 1) ? ((m.T - 1) & 15) : 15;
+    int n_moves = 0;
+    const int from = hfa_walk_row(ws.bp + m.bp_off + (int64_t)w * m.Sp, s, tt, false,
+                                  [&](int, int) { ++n_moves; }, [](int, int, int) {});
+    ws.jump[m.bp_off + idx] = (uint8_t)(s - from);
+    ws.moves[m.bp_off + idx] = (uint8_t)n_moves;
+}
+
 __global__ void __launch_bounds__(HFA_BT_WARPS * 32)
 hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResultPtrs res,
                      float *__restrict__ frame_conf, float *__restrict__ dp_path,
@@ -51,6 +99,7 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         }
         return;
     }
+    if (m.dp_off >= 0) return;                 // kept dp + jump tables: hfa_backtrace_tables_kernel
     const int T = m.T, S = m.S, Sp = m.Sp;
     const int32_t *ids = ws.ids + m.seg_off;
     const uint32_t *bp = ws.bp + m.bp_off;
@@ -149,39 +198,7 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     // states two rounds ahead, emissions one round ahead), then the f32/f64 chain itself runs once
     // per frame, uniformly, over operands parked in shared memory.
     double log_sum = 0.0;
-    if (m.dp_off >= 0) {
-        // the forward pass kept dp for this utterance (banded routing): dp[t, s_t] is a gather, four
-        // frames per lane in flight, no serial chain
-        const float *dps = ws.dp_store + m.dp_off;
-        float carry = 0.0f;                                  // dp_path[-1] := 0 (:286)
-        for (int base = 0; base < T; base += 128) {
-            int stq[4];
-            float dq[4];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const int t = base + 32 * qq + lane;
-                stq[qq] = (t < T) ? path_state[t] : 0;
-            }
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const int t = base + 32 * qq + lane;
-                dq[qq] = (t < T) ? dps[(int64_t)t * Sp + stq[qq]] : 0.0f;
-            }
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const int t = base + 32 * qq + lane;
-                float prev = __shfl_up_sync(0xffffffffu, dq[qq], 1);
-                if (lane == 0) prev = carry;
-                carry = __shfl_sync(0xffffffffu, dq[qq], 31);
-                if (t < T) {
-                    const float fc = expf(__fsub_rn(dq[qq], prev));          // :284-288
-                    if (frame_conf != nullptr) frame_conf[m.frame_off + t] = fc;
-                    if (dp_path != nullptr) dp_path[m.frame_off + t] = dq[qq];
-                    log_sum += (double)logf(__fadd_rn(fc, 1e-6f));           // :97
-                }
-            }
-        }
-    } else {
+    {
     const float *emis = ws.emis + m.emis_off;
     const float2 *edge2 = ws.edge2 + m.edge_off;
     const double ratio = __ddiv_rn((double)T, (double)S);
@@ -340,6 +357,168 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backtrace of the utterances whose forward pass kept dp (latency plans): ONE CTA per utterance.
+// Everything except the row-to-row chain is data parallel; the kernel is bound by the number of
+// dependent memory round trips, so every phase is as wide as the CTA:
+//   1a (warp 0)  entry state of every 16-frame row: one jump-table lookup per row, 16 rows per round
+//                (lane l prefetches jump[w - r][s - l] and jump[w - r][s - l - 32] for the next 16 rows,
+//                the rows are then chained with shuffles);
+//   1b (thread = row)  segment counts from the move table, a CTA-wide scan for their positions, then
+//                every thread re-walks its own row, writes its segments straight in forward order and
+//                gathers dp[t, s_t] of its 16 frames;
+//   2  (thread = frame)  frame confidence, log-sum;   3 (thread = segment)  seconds.
+// ---------------------------------------------------------------------------------------------
+#define HFA_BTT_THREADS 256
+
+__global__ void __launch_bounds__(HFA_BTT_THREADS)
+hfa_backtrace_tables_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResultPtrs res,
+                            float *__restrict__ frame_conf, float *__restrict__ dp_path, double frame_length)
+{
+    constexpr int NW = HFA_BTT_THREADS / 32;
+    __shared__ int warp_sum[NW];
+    __shared__ double warp_log[NW];
+    __shared__ int carry_sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = order[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    if (m.status != 0 || m.dp_off < 0) return;
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    const int32_t *ids = ws.ids + m.seg_off;
+    const uint32_t *bp = ws.bp + m.bp_off;
+    int32_t *path_state = ws.path_state + m.frame_off;
+    int32_t *out_idx = res.ph_idx_seq + m.seg_off;
+    int32_t *out_t = res.ph_time_int + m.seg_off;
+    const int n_rows = (T + 15) >> 4;
+    int32_t *entry = ws.row_entry + m.edge_off / HFA_TILE_T;
+
+    // ---- end state (:269-272) ----
+    const float last1 = ws.dp_last[2 * u];
+    const float last2 = (S >= 2) ? ws.dp_last[2 * u + 1] : HFA_NEG_INF;
+    int s_end = S - 1;
+    float final_score = last1;
+    if (S >= 2 && last2 > last1 && ids[S - 1] == 0) {
+        s_end = S - 2;
+        final_score = last2;
+    }
+
+    // ---- 1a ----
+    if (warp == 0) {
+        const uint8_t *J = ws.jump + m.bp_off;
+        int sr = s_end;
+        int w = n_rows - 1;
+        while (w >= 0) {
+            uint32_t c0[16], c1[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const bool row_ok = w - r >= 1;                  // row 0 has no predecessor row
+                c0[r] = (row_ok && sr - lane >= 0) ? J[(int64_t)(w - r) * Sp + (sr - lane)] : 0u;
+                c1[r] = (row_ok && sr - lane - 32 >= 0) ? J[(int64_t)(w - r) * Sp + (sr - lane - 32)] : 0u;
+            }
+            const int s_ref = sr;
+            int done = 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int d = s_ref - sr;
+                if (w - r < 0 || d >= 64) break;                 // uniform: out of rows / out of the band
+                if (lane == 0) entry[w - r] = sr;
+                const uint32_t x0 = __shfl_sync(0xffffffffu, c0[r], d & 31);
+                const uint32_t x1 = __shfl_sync(0xffffffffu, c1[r], d & 31);
+                sr -= (int)(d < 32 ? x0 : x1);
+                ++done;
+            }
+            w -= done;
+        }
+    }
+    if (tid == 0) carry_sm = 0;
+    __syncthreads();
+
+    // ---- 1b ----
+    const uint8_t *M = ws.moves + m.bp_off;
+    const float *dps = ws.dp_store + m.dp_off;
+    for (int base = 0; base < n_rows; base += HFA_BTT_THREADS) {
+        const int wr = base + tid;
+        int e = 0, c = 0;
+        if (wr < n_rows) {
+            e = entry[wr];
+            c = (int)M[(int64_t)wr * Sp + e] + (wr == 0 ? 1 : 0);
+        }
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        int pos = carry_sm + incl;                               // segments of the rows <= wr
+        for (int q = 0; q < warp; ++q) pos += warp_sum[q];
+        __syncthreads();
+        if (tid == HFA_BTT_THREADS - 1) carry_sm = pos;
+        if (wr < n_rows) {
+            const int tt = (wr == n_rows - 1) ? ((T - 1) & 15) : 15;
+            hfa_walk_row(bp + (int64_t)wr * Sp, e, tt, wr == 0,
+                         [&](int st, int f) {
+                             --pos;
+                             if (pos < S) {
+                                 out_idx[pos] = st;
+                                 out_t[pos] = 16 * wr + f;
+                             }
+                         },
+                         [&](int st, int f_lo, int f_hi) {
+                             for (int f = f_lo; f <= f_hi; ++f) path_state[16 * wr + f] = st;
+                         });
+            // dp[t, s_t] of the row's frames: sixteen independent gathers, parked where the
+            // per-frame state was (phase 2 only needs the dp values)
+            float dv[16];
+#pragma unroll
+            for (int f = 0; f < 16; ++f) {
+                const int t = min(16 * wr + f, T - 1);
+                dv[f] = dps[(int64_t)t * Sp + path_state[t]];
+            }
+#pragma unroll
+            for (int f = 0; f < 16; ++f)
+                if (16 * wr + f < T) path_state[16 * wr + f] = __float_as_int(dv[f]);
+        }
+        __syncthreads();
+    }
+    const int n_seg = min(carry_sm, S);
+
+    // ---- 2: frame confidence (:284-288), total confidence (:97) ----
+    double log_sum = 0.0;
+    for (int t = tid; t < T; t += HFA_BTT_THREADS) {
+        const float cur = __int_as_float(path_state[t]);
+        const float prev = (t > 0) ? __int_as_float(path_state[t - 1]) : 0.0f;   // dp_path[-1] := 0 (:286)
+        const float fc = expf(__fsub_rn(cur, prev));
+        if (frame_conf != nullptr) frame_conf[m.frame_off + t] = fc;
+        if (dp_path != nullptr) dp_path[m.frame_off + t] = cur;
+        log_sum += (double)logf(__fadd_rn(fc, 1e-6f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) log_sum += __shfl_xor_sync(0xffffffffu, log_sum, o);
+    if (lane == 0) warp_log[warp] = log_sum;
+
+    // ---- 3: segments -> seconds ----
+    const float *p = ws.edge_p + m.edge_off;
+    double *out_iv = res.intervals + 2 * m.seg_off;
+    for (int k = tid; k < n_seg; k += HFA_BTT_THREADS) {
+        out_iv[2 * k] = seg_time(p, out_t[k], T, frame_length);
+        out_iv[2 * k + 1] = (k + 1 < n_seg) ? seg_time(p, out_t[k + 1], T, frame_length)
+                                            : __dmul_rn(frame_length, (double)T);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int q = 0; q < NW; ++q) tot += warp_log[q];
+        const float mean = (float)(tot / (double)T);
+        res.status[u] = (final_score == HFA_NEG_INF) ? 4 : 0;
+        res.n_seg[u] = n_seg;
+        res.end_state[u] = s_end;
+        res.final_score[u] = final_score;
+        res.total_conf[u] = expf(__fdiv_rn(mean, 3.0f));
+    }
+}
+
 // test helper: unpack one utterance's backpointers to int8 [T][S] (row 0 = -1, :247)
 __global__ void hfa_unpack_bp_kernel(HfaWs ws, int u, int8_t *__restrict__ out)
 {
@@ -364,6 +543,23 @@ cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, in
     const int blocks = (n + HFA_BT_WARPS - 1) / HFA_BT_WARPS;
     hfa_backtrace_kernel<<<blocks, HFA_BT_WARPS * 32, 0, c.stream>>>(c.ws, order, n, res, frame_conf,
                                                                     dp_path, c.frame_length);
+    return cudaGetLastError();
+}
+
+cudaError_t hfa_launch_jump_tables(const HfaLaunchCtx &c, int n_blocks)
+{
+    if (n_blocks <= 0) return cudaSuccess;
+    hfa_jump_table_kernel<<<n_blocks, 256, 0, c.stream>>>(c.ws);
+    return cudaGetLastError();
+}
+
+// one CTA per utterance of the list; utterances without kept dp are left to hfa_launch_backtrace
+cudaError_t hfa_launch_backtrace_tables(const HfaLaunchCtx &c, const int32_t *order, int n,
+                                        const HfaResultPtrs &res, float *frame_conf, float *dp_path)
+{
+    if (n <= 0) return cudaSuccess;
+    hfa_backtrace_tables_kernel<<<n, HFA_BTT_THREADS, 0, c.stream>>>(c.ws, order, n, res, frame_conf, dp_path,
+                                                                    c.frame_length);
     return cudaGetLastError();
 }
 

@@ -65,6 +65,12 @@ struct HfaWs {
     int32_t *rev_t;              // [sum S]
     float *dp_last;              // end-of-forward scores: [n_utt][2] = dp[T-1][S-1], dp[T-1][S-2]
     float *dp_store;             // dp[t][s] of the utterances with dp_off >= 0 (small-batch routing only)
+    // backtrace jump tables of those utterances (same indexing as bp: one entry per backpointer word)
+    uint8_t *jump;               // states the path drops while it crosses the 16-frame row, entered at s
+    uint8_t *moves;              // segments it opens on the way
+    int32_t *row_entry;          // [sum ceil(T/16)] state of the best path at the last frame of each row
+    const int32_t *jblk_utt;     // utterance of every 256-word block of the jump-table kernel
+    const int32_t *jblk_first;   // [n_utt + 1] first such block of every utterance
     const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
     int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
     uint4 *band_xchg;            // {dp, tag, p.lo, tag}{p.hi, tag, 0, tag} of a band's last 32 states per tile;
