@@ -339,7 +339,10 @@ def main():
                 k = i % n_sets
                 al = HostBatchAligner(T, S, ids_cat, V, synth.FRAME_SECONDS, V + 2,
                                       n_chunks=args.e2e_chunks or None, device=dev, pool=pool)
-                return al.run(heads_host[k])
+                out = al.run(heads_host[k])
+                if not out.all_ok():             # the step's results are read on the host, every step
+                    raise RuntimeError("e2e: an utterance was not aligned")
+                return out
 
             for i in range(3):
                 e2e_step(i)
@@ -426,8 +429,8 @@ def main():
                    "cells_per_gpu": int(m["cells"]), "frames_per_gpu": int(m["frames"]),
                    "frame_seconds": synth.FRAME_SECONDS, "sharding": "utterances by rank, no collective",
                    "collation": "batch packed longest utterance first",
-                   "e2e_pipeline": "contiguous chunks (30/28/22/12/8 % of the bytes): DMA of chunk i+1 overlaps "
-                                   "collation and kernels of chunk i",
+                   "e2e_pipeline": "upload cut by rows (30/28/22/12/8 % of the bytes): the DMA of piece i+1 overlaps "
+                                   "collation and kernels of the utterances completed by piece i",
                    "l2": f"{m['n_sets']} rotating input+workspace sets of {m['bytes_per_set'] / 1e6:.0f} MB "
                          "(consecutive steps touch different memory; total > 126 MB L2)"},
         "clocks": m["clk"], "e2e": m["e2e"], "gpu_launches": int(m["launches"]),

@@ -75,8 +75,80 @@ class BufferPool:
 class _Chunk:
     """Static description of one contiguous utterance range (everything that does not depend on the
     logits is prepared once, in HostBatchAligner.__init__)."""
-    __slots__ = ("b0", "b1", "r0", "r1", "T", "S", "ids", "seg_off", "frame_ptr_off", "edge_ptr_off", "stride",
+    __slots__ = ("b0", "b1", "piece", "T", "S", "ids", "seg_off", "frame_ptr_off", "edge_ptr_off", "stride",
                  "ones", "stream")
+
+
+class PipelineResult(dict):
+    """What ``HostBatchAligner.run`` returns: a dict whose per-utterance arrays (``status``, ``n_seg``,
+    ``total_conf``, ``final_score``) and per-chunk ragged views (``chunks``) are cut out of the pinned
+    result blobs on first access -- the blobs are on the host when ``run`` returns, the Python-side
+    slicing is not part of the critical path of a pipeline that only needs some of them."""
+
+    def __init__(self, n_utt, live, lib):
+        super().__init__()
+        self._n, self._live, self._lib = n_utt, live, lib
+        self.d2h_bytes = sum(int(item[2].total_bytes) for item in live)
+
+    def _materialise(self):
+        if self._live is None:
+            return
+        n = self._n
+        out = dict(status=np.empty(n, np.int32), n_seg=np.empty(n, np.int32), total_conf=np.empty(n, np.float32),
+                   final_score=np.empty(n, np.float32), chunks=[])
+        for c, h, lay, host_res, _, _ in self._live:
+            blob = host_res.numpy()
+            m, ns = c.b1 - c.b0, int(c.seg_off[-1])
+
+            def v(off, dtype, count, blob=blob):
+                return blob[off:off + count * np.dtype(dtype).itemsize].view(dtype)
+
+            views = dict(status=v(lay.status, np.int32, m), n_seg=v(lay.n_seg, np.int32, m),
+                         end_state=v(lay.end_state, np.int32, m), final_score=v(lay.final_score, np.float32, m),
+                         total_conf=v(lay.total_conf, np.float32, m), ph_idx_seq=v(lay.ph_idx_seq, np.int32, ns),
+                         ph_time_int=v(lay.ph_time_int, np.int32, ns),
+                         intervals=v(lay.intervals, np.float64, 2 * ns).reshape(ns, 2))
+            for k in ("status", "n_seg", "total_conf", "final_score"):
+                out[k][c.b0:c.b1] = views[k]
+            out["chunks"].append((c.b0, c.b1, c.seg_off, views))
+        self._release()
+        dict.update(self, out)
+
+    def all_ok(self) -> bool:
+        """True when every utterance was aligned (status 0) -- reads the status words straight out
+        of the pinned result blobs, without building the per-utterance arrays."""
+        if self._live is None:
+            return bool((dict.__getitem__(self, "status") == 0).all())
+        for c, _, lay, host_res, _, _ in self._live:
+            m = c.b1 - c.b0
+            if host_res.numpy()[lay.status:lay.status + 4 * m].view(np.int32).any():
+                return False
+        return True
+
+    def _release(self):
+        if self._live is not None:
+            for item in self._live:
+                self._lib.hfa_plan_destroy(item[1])
+            self._live = None
+
+    def __getitem__(self, key):
+        if not dict.__contains__(self, key):
+            self._materialise()
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        self._materialise()
+        return dict.__contains__(self, key)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
 
 class HostBatchAligner:
@@ -86,10 +158,12 @@ class HostBatchAligner:
     ph_ids: concatenated phoneme ids; frame_col / edge_col: first column of the V frame logits and
     the column of the edge logit inside a row (networks/task/forced_alignment.py:288-291: 2 and 0).
     The hot path (``run``) talks to the C ABI directly through ctypes: per-chunk host overhead is
-    what bounds the pipeline depth.
+    what bounds the pipeline depth.  The upload is cut by ROWS (byte shares of the packed tensor), so
+    its first piece is on the wire before any per-utterance table exists; utterance chunk c holds the
+    utterances that are complete once piece c has landed.
     """
 
-    # byte shares of the chunks, first to last: the early chunks are big (their alignment overlaps the
+    # byte shares of the pieces, first to last: the early ones are big (their alignment overlaps the
     # rest of the upload anyway), the last one is small so that little is left when the upload ends
     DEFAULT_SHARES = (0.30, 0.28, 0.22, 0.12, 0.08)
 
@@ -111,41 +185,48 @@ class HostBatchAligner:
         if shares is None:
             shares = self.DEFAULT_SHARES if n_chunks is None else [1.0 / max(int(n_chunks), 1)] * max(int(n_chunks), 1)
         self.shares = np.asarray(shares, dtype=np.float64) / float(np.sum(shares))
-        # only what the upload itself needs is computed here; the per-chunk tables are built in run()
-        # while the first chunks are already on the wire
-        self.row_off = np.concatenate([[0], np.cumsum(self.T.astype(np.int64))])
-        cuts = np.searchsorted(self.row_off[1:], self.row_off[-1] * np.cumsum(self.shares)[:-1]) + 1
-        self.bounds = np.unique(np.concatenate([[0], np.minimum(cuts, self.n_utt), [self.n_utt]]))
+        self.total_rows = int(self.T.sum(dtype=np.int64))
+        # rows at which the upload is cut (the last piece ends at total_rows)
+        cuts = np.minimum((self.total_rows * np.cumsum(self.shares)).astype(np.int64), self.total_rows)
+        cuts[-1] = self.total_rows
+        self.row_cuts = [int(x) for x in cuts]
         self.chunks = None
         self.pool = pool if pool is not None else BufferPool(self.dev)
-        self.h2d_bytes = int(self.row_off[-1]) * self.row_width * self.esz
+        self.h2d_bytes = self.total_rows * self.row_width * self.esz
         self.d2h_bytes = 0
 
     def _build_chunks(self):
         W, esz = self.row_width, self.esz
+        row_off = np.concatenate([[0], np.cumsum(self.T.astype(np.int64))])
         seg_off = np.concatenate([[0], np.cumsum(np.maximum(self.S, 0).astype(np.int64))])
+        # utterance b is complete when the piece that holds its last row has landed
+        ends = np.searchsorted(row_off[1:], np.asarray(self.row_cuts, dtype=np.int64), side="right")
+        ends[-1] = self.n_utt
         self.chunks = []
-        for ci in range(len(self.bounds) - 1):
+        b0 = 0
+        for ci, b1 in enumerate(int(e) for e in ends):
+            if b1 <= b0:
+                continue
             c = _Chunk()
-            c.b0, c.b1 = int(self.bounds[ci]), int(self.bounds[ci + 1])
-            c.r0, c.r1 = int(self.row_off[c.b0]), int(self.row_off[c.b1])
-            c.T = np.ascontiguousarray(self.T[c.b0:c.b1])
-            c.S = np.ascontiguousarray(self.S[c.b0:c.b1])
-            c.ids = np.ascontiguousarray(self.ids[seg_off[c.b0]:seg_off[c.b1]])
-            c.seg_off = seg_off[c.b0:c.b1 + 1] - seg_off[c.b0]
-            rows = self.row_off[c.b0:c.b1] - c.r0
+            c.b0, c.b1, c.piece = b0, b1, ci
+            c.T = np.ascontiguousarray(self.T[b0:b1])
+            c.S = np.ascontiguousarray(self.S[b0:b1])
+            c.ids = np.ascontiguousarray(self.ids[seg_off[b0]:seg_off[b1]])
+            c.seg_off = seg_off[b0:b1 + 1] - seg_off[b0]
+            rows = row_off[b0:b1]
             c.frame_ptr_off = np.ascontiguousarray((rows * W + self.frame_col) * esz)
             c.edge_ptr_off = np.ascontiguousarray((rows * W + self.edge_col) * esz)
-            c.stride = np.full(c.b1 - c.b0, W, dtype=np.int64)
-            c.ones = np.ones(c.b1 - c.b0, dtype=np.int64)
+            c.stride = np.full(b1 - b0, W, dtype=np.int64)
+            c.ones = np.ones(b1 - b0, dtype=np.int64)
             c.stream = _side_stream(self.dev, 1 + ci)
             self.chunks.append(c)
+            b0 = b1
 
     def run(self, head_host: torch.Tensor, profile: bool = False) -> dict:
         """head_host: pinned host tensor [sum T, row_width].  Returns per-utterance arrays
         (status, n_seg, total_conf, final_score) plus the per-chunk ragged views."""
         if head_host.is_cuda or head_host.dtype != self.dtype or head_host.dim() != 2 \
-                or head_host.shape[1] != self.row_width or head_host.shape[0] < self.row_off[-1]:
+                or head_host.shape[1] != self.row_width or head_host.shape[0] < self.total_rows:
             raise ValueError("head_host must be a host tensor [sum T, row_width] of the configured dtype")
         import ctypes as C
         import time
@@ -160,21 +241,24 @@ class HostBatchAligner:
             if profile:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record(cur)
-            # 1. every chunk goes on the wire, in order, before any host-side collation
-            staged = []
+            # 1. every piece goes on the wire, in order, before any host-side collation
+            dev_head = pool.device_bytes(max(self.total_rows, 1) * W * esz).view(self.dtype).view(-1, W)
+            landed = []
             with torch.cuda.stream(copy_stream):
-                for ci in range(len(self.bounds) - 1):
-                    r0, r1 = int(self.row_off[self.bounds[ci]]), int(self.row_off[self.bounds[ci + 1]])
-                    dev_head = pool.device_bytes(max(r1 - r0, 1) * W * esz).view(self.dtype).view(-1, W)
-                    dev_head[: r1 - r0].copy_(head_host[r0:r1], non_blocking=True)
-                    landed = torch.cuda.Event(enable_timing=profile)
-                    landed.record(copy_stream)
-                    staged.append((dev_head, landed))
+                r0 = 0
+                for r1 in self.row_cuts:
+                    if r1 > r0:
+                        dev_head[r0:r1].copy_(head_host[r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event(enable_timing=profile)
+                    ev.record(copy_stream)
+                    landed.append(ev)
+                    r0 = r1
             if self.chunks is None:
                 self._build_chunks()
-            # 2. collation + launches of chunk i while the later chunks are still travelling
+            base = dev_head.data_ptr()
+            # 2. collation + launches of chunk i while the later pieces are still travelling
             prof = []
-            for c, (dev_head, landed) in zip(self.chunks, staged):
+            for c in self.chunks:
                 n = c.b1 - c.b0
                 h = C.c_void_p()
                 _lib.check(lib.hfa_plan_create(n, self.vocab_size, c.T.ctypes.data, c.S.ctypes.data,
@@ -187,48 +271,27 @@ class HostBatchAligner:
                 st = c.stream
                 st.wait_stream(cur)
                 sp = int(st.cuda_stream)
-                base = dev_head.data_ptr()
                 fp, ep = c.frame_ptr_off + base, c.edge_ptr_off + base
                 wp = ws.data_ptr()
                 _lib.check(lib.hfa_plan_upload(h, wp, sp), "hfa_plan_upload")
                 _lib.check(lib.hfa_set_inputs(h, wp, fp.ctypes.data, c.stride.ctypes.data, c.ones.ctypes.data,
                                               ep.ctypes.data, c.stride.ctypes.data, sp), "hfa_set_inputs")
-                st.wait_event(landed)
+                st.wait_event(landed[c.piece])
                 _lib.check(lib.hfa_align_batch(h, wp, self.dt, res.data_ptr(), None, sp), "hfa_align_batch")
                 with torch.cuda.stream(st):
                     host_res.copy_(res, non_blocking=True)
                     if profile:
                         done = torch.cuda.Event(enable_timing=True)
                         done.record(st)
-                        prof.append((landed, done, time.perf_counter() - t_host0))
+                        prof.append((landed[c.piece], done, time.perf_counter() - t_host0))
                 live.append((c, h, lay, host_res, ws, res))
             for item in live:
                 item[0].stream.synchronize()
-        n = self.n_utt
-        out = dict(status=np.empty(n, np.int32), n_seg=np.empty(n, np.int32), total_conf=np.empty(n, np.float32),
-                   final_score=np.empty(n, np.float32), chunks=[])
-        d2h = 0
-        for c, h, lay, host_res, _, _ in live:
-            blob = host_res.numpy()
-            m, ns = c.b1 - c.b0, int(c.seg_off[-1])
-
-            def v(off, dtype, count, blob=blob):
-                return blob[off:off + count * np.dtype(dtype).itemsize].view(dtype)
-
-            views = dict(status=v(lay.status, np.int32, m), n_seg=v(lay.n_seg, np.int32, m),
-                         end_state=v(lay.end_state, np.int32, m), final_score=v(lay.final_score, np.float32, m),
-                         total_conf=v(lay.total_conf, np.float32, m), ph_idx_seq=v(lay.ph_idx_seq, np.int32, ns),
-                         ph_time_int=v(lay.ph_time_int, np.int32, ns),
-                         intervals=v(lay.intervals, np.float64, 2 * ns).reshape(ns, 2))
-            for k in ("status", "n_seg", "total_conf", "final_score"):
-                out[k][c.b0:c.b1] = views[k]
-            out["chunks"].append((c.b0, c.b1, c.seg_off, views))
-            d2h += int(lay.total_bytes)
-            lib.hfa_plan_destroy(h)
-        self.d2h_bytes = d2h
+        out = PipelineResult(self.n_utt, live, lib)
+        self.d2h_bytes = out.d2h_bytes
         if profile:
-            out["profile"] = [dict(landed_ms=ev0.elapsed_time(l), done_ms=ev0.elapsed_time(d), host_issued_ms=1e3 * t)
-                              for l, d, t in prof]
+            dict.__setitem__(out, "profile", [dict(landed_ms=ev0.elapsed_time(l), done_ms=ev0.elapsed_time(d),
+                                                   host_issued_ms=1e3 * t) for l, d, t in prof])
         return out
 
     @staticmethod

@@ -270,7 +270,7 @@ def test_host_pipeline_matches_decode_batch():
         for _ in range(2):                      # second pass reuses the pooled buffers
             al = HostBatchAligner(T, S, ids_cat, V, dec.frame_length, V + 2, n_chunks=n_chunks, pool=pool)
             out = al.run(head)
-            assert (out["status"] == 0).all()
+            assert out.all_ok() and (out["status"] == 0).all()
             for b in range(len(items)):
                 idx, tim, iv = al.segments(out, b)
                 ridx, rtim, riv = ref.segments(b)
