@@ -352,8 +352,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 // cell more HBM traffic, irrelevant there) so that the backtrace reads dp[t, s_t]
                 // instead of re-running the serial chain along the path
                 if (keep_dp) {
+                    p->utt[b].band_k = k;
                     p->utt[b].dp_off = p->dp_store_elems;
-                    p->dp_store_elems += (int64_t)p->utt[b].T * p->utt[b].Sp;
+                    p->dp_store_elems += (int64_t)nb * p->utt[b].T * 32 * k;    // one [T][32 k] block per band
                 }
                 for (int j = 0; j < nb; ++j) {
                     const bool has_right = j + 1 < nb;

@@ -474,7 +474,7 @@ hfa_backtrace_tables_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, 
 #pragma unroll
             for (int f = 0; f < 16; ++f) {
                 const int t = min(16 * wr + f, T - 1);
-                dv[f] = dps[(int64_t)t * Sp + path_state[t]];
+                dv[f] = dps[hfa_dp_store_index(m.band_k, T, t, path_state[t])];
             }
 #pragma unroll
             for (int f = 0; f < 16; ++f)

@@ -29,9 +29,10 @@ struct HfaUtt {                  // 80 bytes, one per utterance, device copy liv
     int64_t bp_off;              // u32 words
     int64_t frame_off;           // frames, unpadded (frame_conf / dp_path / path_state / dense in)
     int64_t cell_off;            // sum of T*S of the previous utterances (dense ragged dumps)
-    int64_t dp_off;              // floats into dp_store ([t][Sp] like emis) when the forward pass keeps
-                                 // dp for this utterance (banded routing), else -1
-    int64_t reserved;
+    int64_t dp_off;              // floats into dp_store when the forward pass keeps dp for this utterance
+                                 // (banded routing; one [T][32 K] block per band, hfa_dp_store_index), else -1
+    int32_t band_k;              // states per lane of that banded pass (2 / 4 / 8)
+    int32_t reserved;
 };
 static_assert(sizeof(HfaUtt) == 80, "HfaUtt is 80 bytes (16-byte multiple)");
 
@@ -78,6 +79,16 @@ struct HfaWs {
 };
 
 #define HFA_NEG_INF __uint_as_float(0xff800000u)
+
+// index of dp[t][s] inside an utterance's part of the dp store (floats from dp_off).  The banded kernel
+// with K states per lane has windows of W = 32 K states at a stride of W - 32, and every band keeps its
+// whole window as a [T][W] block; state s is OWNED by band 0 if s < W, else by band 1 + (s - W) / (W - 32).
+__host__ __device__ __forceinline__ int64_t hfa_dp_store_index(int K, int T, int t, int s)
+{
+    const int W = 32 * K, OWN = W - 32;
+    const int b = (s < W) ? 0 : 1 + (s - W) / OWN;
+    return ((int64_t)b * T + t) * W + (s - b * OWN);
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP)

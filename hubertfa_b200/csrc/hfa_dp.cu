@@ -916,19 +916,18 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         }
         uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + 2 * lane;
         // dp store: the compute warp leaves dp[t][.] of a tile in the stage it has just consumed (in
-        // place of the emissions); before the stage is refilled its owned columns go out as one
-        // bulk store per frame row.
-        const int own0 = has_left ? 32 : 0;                    // first owned column of the window
-        float *g_dp = (KEEP && m.dp_off >= 0 && cols > own0) ? ws.dp_store + m.dp_off + c0 + own0 : nullptr;
-        const uint32_t own_b = (uint32_t)(cols - own0) * 4u;
+        // place of the emissions); before the stage is refilled the tile goes out as one bulk store.
+        // every band keeps its WHOLE window ([T][W] block of its own, the halo columns included --
+        // they hold stale values and are never read) so that a tile leaves as one bulk store
+        float *g_dp = (KEEP && m.dp_off >= 0) ? ws.dp_store + m.dp_off + (int64_t)band * T * W : nullptr;
         for (int i = 0; i < n_tiles + NST; ++i) {
             const int st = i % NST;
             if (i >= NST) {
                 hfa_mbar_wait(&empty[st], (uint32_t)(((i / NST) - 1) & 1));
                 const int j = i - NST;                         // the tile that sat in this stage
-                if (g_dp != nullptr && lane < min(TT, T - j * TT)) {
-                    hfa_bulk_store(g_dp + (int64_t)(j * TT + lane) * Sp, tile0 + st * TILE_FLOATS + lane * W + own0,
-                                   own_b);
+                if (g_dp != nullptr && lane == 0) {
+                    hfa_bulk_store(g_dp + (int64_t)j * TT * W, tile0 + st * TILE_FLOATS,
+                                   (uint32_t)min(TT, T - j * TT) * (uint32_t)W * 4u);
                     hfa_bulk_commit();
                     hfa_bulk_wait_read();                      // the stage may be overwritten
                 }
