@@ -344,6 +344,10 @@ class AlignmentDecoder:
         return object.__getattribute__(self, name)
 
     def ctc(self):
+        src = getattr(self, "_ctc_src", None)
+        if src is not None and src.is_cuda:            # same result, argmax + collapse on the device
+            x = src.squeeze(0) if src.dim() == 3 else src
+            return ops.ctc_greedy(x).cpu().numpy().astype(np.int64)
         ctc = np.argmax(self.ctc_logits, axis=-1)                                  # ad:145-150
         ctc_index = np.concatenate([[0], ctc])
         ctc_index = (ctc_index[1:] != ctc_index[:-1]) * ctc != 0

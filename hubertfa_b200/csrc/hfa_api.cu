@@ -2,6 +2,7 @@
 // declared in include/hfa_align.h.  No torch types, no device allocation, no stream sync.
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,8 @@ cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const f
 cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
                                  const HfaResultPtrs &res, float *frame_conf, float *dp_path);
 cudaError_t hfa_launch_unpack_bp(const HfaLaunchCtx &c, int utt, int8_t *out);
+cudaError_t hfa_launch_ctc_greedy(const void *logits, int dtype, int T, int V, int64_t st_t, int64_t st_v,
+                                  int32_t *arg, int32_t *out_ids, int32_t *out_len, cudaStream_t stream);
 cudaError_t hfa_launch_jump_tables(const HfaLaunchCtx &c, int n_blocks);
 cudaError_t hfa_launch_backtrace_tables(const HfaLaunchCtx &c, const int32_t *order, int n,
                                         const HfaResultPtrs &res, float *frame_conf, float *dp_path);
@@ -811,6 +814,19 @@ int hfa_align_batch(const hfa_plan *p, void *workspace, int32_t dtype, void *res
     }
     if (rc != HFA_OK) return rc;
     return hfa_backtrace(p, workspace, result, frame_conf, nullptr, stream);
+}
+
+int hfa_ctc_greedy(const void *logits, int32_t dtype, int64_t T, int64_t V, int64_t stride_t,
+                   int64_t stride_v, int32_t *scratch, int32_t *out_ids, int32_t *out_len, void *stream)
+{
+    if (!logits || !scratch || !out_ids || !out_len) return fail(HFA_ERR_ARG, "hfa_ctc_greedy: NULL argument");
+    if (T < 0 || V < 1 || T > INT32_MAX || V > INT32_MAX || dtype < 0 || dtype > 2)
+        return fail(HFA_ERR_ARG, "hfa_ctc_greedy: bad shape / dtype (T=%lld, V=%lld)", (long long)T, (long long)V);
+    cudaError_t e = hfa_launch_ctc_greedy(logits, dtype, (int)T, (int)V, stride_t, stride_v, scratch, out_ids,
+                                          out_len, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_ctc_greedy: launch");
+    g_launches += 1;
+    return HFA_OK;
 }
 
 int hfa_debug_unpack_backptr(const hfa_plan *p, const void *workspace, int32_t utt, int8_t *out,

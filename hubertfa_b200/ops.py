@@ -215,3 +215,22 @@ def launch_count() -> int:
 
 TORCH_TO_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16,
                   torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def ctc_greedy(logits: torch.Tensor) -> torch.Tensor:
+    """Greedy CTC decode of one utterance on the device (alignment_decoder.py:145-150).
+    logits: CUDA tensor [T, V] (any strides; f32 / f16 / bf16).  Returns the int32 id sequence."""
+    if logits.dim() != 2 or not logits.is_cuda:
+        raise HfaError("ctc_greedy expects a CUDA tensor [T, V]")
+    if logits.dtype not in TORCH_TO_DTYPE:
+        logits = logits.float()
+    T, V = int(logits.shape[0]), int(logits.shape[1])
+    dev = logits.device
+    scratch = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    out = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().hfa_ctc_greedy(logits.data_ptr(), TORCH_TO_DTYPE[logits.dtype], T, V, logits.stride(0),
+                                         logits.stride(1), scratch.data_ptr(), out.data_ptr(), n.data_ptr(),
+                                         _stream_ptr()), "hfa_ctc_greedy")
+    return out[: int(n.item())]

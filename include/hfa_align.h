@@ -153,6 +153,14 @@ int hfa_forward_fused(const hfa_plan *plan, void *workspace, int32_t dtype, void
 /* algorithmic HBM bytes of that pass: logits + edge logits in, edge logs + backpointers + dp out */
 int64_t hfa_plan_algorithmic_bytes_fused(const hfa_plan *plan, int32_t dtype);
 
+/* ---- greedy CTC decode (alignment_decoder.py:145-150, the validation-time ctc()) ------------ */
+/* logits: [dev] [T][V] addressed as base[t*stride_t + v*stride_v] (elements), dtype HFA_DTYPE_*.
+ * scratch / out_ids: [dev] int32 [T] each; out_len: [dev] int32.  out_ids[0 .. *out_len) = the
+ * argmax ids of the frames where the argmax changes (the frame before frame 0 counts as id 0) and
+ * is not 0 -- what ctc() returns.  Ties in the argmax go to the lowest id (numpy). */
+int hfa_ctc_greedy(const void *logits, int32_t dtype, int64_t T, int64_t V, int64_t stride_t,
+                   int64_t stride_v, int32_t *scratch, int32_t *out_ids, int32_t *out_len, void *stream);
+
 /* ---- introspection for tests: unpacked backpointers of one utterance ------------------------ */
 /* out: [dev] int8 [T_b][S_b], codes 0/1/2 (row 0 is -1 like the reference, :247). */
 int hfa_debug_unpack_backptr(const hfa_plan *plan, const void *workspace, int32_t utt, int8_t *out,

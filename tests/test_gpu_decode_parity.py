@@ -336,3 +336,30 @@ def test_fused_forward_equals_three_stage_route():
         idx, tim, _ = r.segments(b)
         o, k = int(r.seg_off[b]), int(v["n_seg"][b])
         assert np.array_equal(idx, v["ph_idx_seq"][o:o + k]) and np.array_equal(tim, v["ph_time_int"][o:o + k])
+
+
+def test_ctc_greedy_kernel_matches_numpy():
+    """hfa_ctc_greedy vs the reference's three numpy lines (alignment_decoder.py:145-150): ties in the
+    argmax (first maximum), strided views, half precisions, T = 1, all-blank, long T."""
+    from hubertfa_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for T, V in [(1, 5), (7, 39), (300, 63), (1500, 74), (5000, 200), (33, 2)]:
+        x = torch.randn(T, V, generator=g)
+        cases.append(x)
+        cases.append(torch.round(x * 2) / 2)                      # coarse grid: many exact ties
+    cases.append(torch.zeros(40, 10))                             # all ties -> id 0 everywhere -> empty
+    blank = torch.randn(50, 12, generator=g)
+    blank[:, 0] += 100                                            # blank wins everywhere
+    cases.append(blank)
+    for x in cases:
+        want = onp.ctc_greedy(x.numpy())
+        got = ops.ctc_greedy(x.cuda()).cpu().numpy()
+        assert np.array_equal(got, want)
+        wide = torch.zeros(x.shape[0], 2 * x.shape[1] + 3)
+        wide[:, 3::2] = x                                         # strided view of a wider tensor
+        got = ops.ctc_greedy(wide.cuda()[:, 3::2]).cpu().numpy()
+        assert np.array_equal(got, want)
+    for dt in (torch.float16, torch.bfloat16):
+        x = torch.randn(400, 63, generator=g).to(dt)
+        assert np.array_equal(ops.ctc_greedy(x.cuda()).cpu().numpy(), onp.ctc_greedy(x.float().numpy()))
