@@ -41,6 +41,10 @@ WORKLOADS = {
     "c3": (1, 63, None, None, "configs[2]: one 10 min utterance, T=30000, S=2000, V=63"),
     "c4": (4096, 74, (5, 30), (20, 150), "configs[3]: 4096 mixed-length utterances, jyutping V=74"),
     "c4j": (4096, 39, (5, 30), (20, 150), "configs[3]: 4096 mixed-length utterances, japanese V=39"),
+    # sizes between configs[1] and configs[3] (routing threshold experiments)
+    "m512": (512, 63, (5, 30), (20, 150), "512 utterances, 5-30 s, 20-150 phonemes, V=63"),
+    "m1024": (1024, 63, (5, 30), (20, 150), "1024 utterances, 5-30 s, 20-150 phonemes, V=63"),
+    "m2048": (2048, 63, (5, 30), (20, 150), "2048 utterances, 5-30 s, 20-150 phonemes, V=63"),
 }
 
 
@@ -229,7 +233,7 @@ def main():
         T, S, V, desc = workload_shapes(workload, seed)
         ids_list = synth.make_ids_batch(T, S, V, seed=seed)
         ids_cat = np.concatenate(ids_list)
-        n_sets = N_SETS if workload != "c4" and workload != "c4j" else 2
+        n_sets = N_SETS if len(T) <= 512 else 2
         heads_host = [make_head(T, V, seed + 17 * i).pin_memory() for i in range(n_sets)]
         heads_dev = [h.to(dev) for h in heads_host]
         plan = ops.AlignPlan(T, S, ids_cat, V, synth.FRAME_SECONDS)
