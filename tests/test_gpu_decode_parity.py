@@ -363,3 +363,63 @@ def test_ctc_greedy_kernel_matches_numpy():
     for dt in (torch.float16, torch.bfloat16):
         x = torch.randn(400, 63, generator=g).to(dt)
         assert np.array_equal(ops.ctc_greedy(x.cuda()).cpu().numpy(), onp.ctc_greedy(x.float().numpy()))
+
+
+@pytest.mark.parametrize("mix", ["unsplit-fused", "split-bands", "with-long-sequences"])
+def test_random_planted_batches_match_the_oracle_in_every_route(mix):
+    """decode_batch (auto routing) on many small random utterances with peaked (planted) logits,
+    head-layout strided views: paths, end states and intervals must equal the C oracle run on the
+    same logits.  The three mixes exercise the fused forward pass (no utterance split), the
+    multi-band route and the route with S > 256 bands."""
+    rng = np.random.default_rng({"unsplit-fused": 1, "split-bands": 2, "with-long-sequences": 3}[mix])
+    n = 120
+    if mix == "unsplit-fused":
+        S = rng.integers(1, 65, n)
+    elif mix == "split-bands":
+        S = rng.integers(1, 257, n)
+    else:
+        S = np.concatenate([rng.integers(1, 257, n - 6), rng.integers(257, 700, 6)])
+    T = np.maximum(rng.integers(1, 400, n), (S * rng.uniform(0.6, 3.0, n)).astype(np.int64))
+    T, S = T.astype(np.int32), S.astype(np.int32)
+    V = 63
+    vocab, items = synth.make_batch(T, S, V, seed=int(rng.integers(1 << 30)), style="dictionary", planted=True)
+    dev = torch.device("cuda")
+    heads = []
+    for it in items:
+        h = torch.zeros(1, it["frame"].shape[1], V + 2)
+        h[0, :, 0] = it["edge"][0]
+        h[0, :, 2:] = it["frame"][0]
+        heads.append(h.to(dev))
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    res = dec.decode_batch([h[:, :, 2:] for h in heads], [h[:, :, 0] for h in heads],
+                           [it["ph_seq"] for it in items], [it["word_seq"] for it in items],
+                           [it["ph_idx_to_word_idx"] for it in items])
+    bad = []
+    for b, it in enumerate(items):
+        e = oc.emission(it["frame"][0].numpy(), it["ids"])
+        p = oc.edge_pred(it["edge"][0].numpy())
+        _, ep = oc.edge_prob(p)
+        el, ne = oc.edge_logs(ep)
+        r = oc.decode(it["ids"], e, el, ne)
+        idx, tim, iv = res.segments(b)
+        if not (np.array_equal(idx, r["ph_idx_seq"]) and np.array_equal(tim, r["ph_time_int"])):
+            bad.append(b)
+            continue
+        assert res.end_state[b] == r["end_state"]
+        want = oc.intervals(int(T[b]), r["ph_time_int"], p, dec.frame_length)
+        np.testing.assert_allclose(iv, want, rtol=0, atol=1e-7)
+        if np.isfinite(r["dp_path"][-1]):
+            assert abs(res.final_score[b] - r["dp_path"][-1]) <= 1e-4 * max(abs(r["dp_path"][-1]), 1.0)
+    # planted logits are peaked; T < S utterances can still sit on exact near-ties of the two
+    # softmax implementations -- those must be reproduced by the oracle DP on OUR emissions
+    for b in bad:
+        it = items[b]
+        plan, ws = _emission_gpu([heads[b][0, :, 2:]], [heads[b][0, :, 0]], [it["ids"]], V)
+        Sp = (int(S[b]) + 3) & ~3
+        e_gpu = _ws_region(plan, ws, "emis").cpu().numpy().reshape(int(T[b]), Sp)[:, :int(S[b])]
+        e2 = _ws_region(plan, ws, "edge2").cpu().numpy()[:int(T[b])]
+        r = oc.decode(it["ids"], np.ascontiguousarray(e_gpu), np.ascontiguousarray(e2[:, 0]),
+                      np.ascontiguousarray(e2[:, 1]))
+        idx, tim, _ = res.segments(b)
+        assert np.array_equal(idx, r["ph_idx_seq"]) and np.array_equal(tim, r["ph_time_int"]), (mix, b)
+    assert len(bad) <= n // 10, f"{len(bad)} of {n} paths differ from the oracle on peaked logits"
