@@ -958,16 +958,17 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                     if (n_kept <= 64) {                                       // warp-uniform
                         float xv[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) xv[j] = (part + 4 * j < n_kept) ? row[kreg[j]] : HFA_NEG_INF;
+                        for (int j = 0; j < 16; ++j) {   // unconditional load (kreg is 0 past the end) + select
+                            const float x = row[kreg[j]];
+                            xv[j] = (part + 4 * j < n_kept) ? x : HFA_NEG_INF;
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) mx = fmaxf(mx, xv[j]);
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) xv[j] = expf(__fsub_rn(xv[j], mx));
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (part + 4 * j < n_kept) sum = __fadd_rn(sum, xv[j]);
+                        for (int j = 0; j < 16; ++j)     // entries past the end are -inf: exp = +0, sum unchanged
+                            sum = __fadd_rn(sum, expf(__fsub_rn(xv[j], mx)));
                     } else {
                         for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, row[kept_sm[k]]);
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));

@@ -244,7 +244,7 @@ hfa_edge_kernel(HfaWs ws)
 // 2 elements in) and is rounded up to 16 bytes; both stay inside the allocation the view lives in.
 // ---------------------------------------------------------------------------------------------
 template <typename TIn>
-__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)
+__global__ void __launch_bounds__(HFA_EMIS_WARPS * 32)      // (.., 4) caps it at 64 registers: measured slower
 hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_bytes)
 {
     constexpr int RPW = HFA_EMIS_ROWS / HFA_EMIS_WARPS;                      // rows per warp
@@ -290,6 +290,9 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
     int cur_u = -1;
     int S = 0, Sp = 4, T = 0, n_kept = 0;
     uint32_t goff[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int kreg[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) kreg[j] = 0;
     HfaUtt m;
     HfaInput in;
     for (int blk = blk0; blk < blk1; ++blk) {
@@ -329,6 +332,11 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
                 goff[it][2] = (uint32_t)id4.z; goff[it][3] = (uint32_t)id4.w;
             }
             __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = (lane & 3) + 4 * j;
+                kreg[j] = (k < n_kept && k < 256) ? kept_sm[k] : 0;
+            }
         }
         const int t_base = (blk - ws.row_blocks[u]) * HFA_EMIS_ROWS;
         const int row_st = (int)in.frame_st;
@@ -343,13 +351,30 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
             const int rr = RPW * warp + (lane >> 2);
             const TIn *row = xs + rr * row_st;
             const int part = lane & 3;
-            float mx = HFA_NEG_INF;
-            for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, hfa_to_float<TIn>(row[kept_sm[k]]));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            float sum = 0.0f;
-            for (int k = part; k < n_kept; k += 4)
-                sum = __fadd_rn(sum, expf(__fsub_rn(hfa_to_float<TIn>(row[kept_sm[k]]), mx)));
+            float mx = HFA_NEG_INF, sum = 0.0f;
+            if (n_kept <= 64) {                                              // CTA-uniform
+                // the lane's kept ids sit in registers (kreg, set up per utterance): one load per
+                // logit, reused by both passes; same order of operations as the loop below
+                float xv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {       // unconditional load (kreg is 0 past the end) + select:
+                    const float x = hfa_to_float<TIn>(row[kreg[j]]);      // no divergent branches
+                    xv[j] = (part + 4 * j < n_kept) ? x : HFA_NEG_INF;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, xv[j]);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+                for (int j = 0; j < 16; ++j)         // entries past the end are -inf: exp = +0, sum unchanged
+                    sum = __fadd_rn(sum, expf(__fsub_rn(xv[j], mx)));
+            } else {
+                for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, hfa_to_float<TIn>(row[kept_sm[k]]));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                for (int k = part; k < n_kept; k += 4)
+                    sum = __fadd_rn(sum, expf(__fsub_rn(hfa_to_float<TIn>(row[kept_sm[k]]), mx)));
+            }
             sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
             sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
             if (part == 0) stat_sm[rr] = make_float2(mx, logf(sum));
@@ -514,7 +539,11 @@ static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_
         e = cudaFuncSetAttribute(hfa_emission_stream_kernel<TIn>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int per_sm = (int)((200 * 1024) / smem);
+        // persistent CTAs: exactly as many as are resident at once (registers and shared memory)
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfa_emission_stream_kernel<TIn>,
+                                                          HFA_EMIS_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
         per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
         const int grid = blocks < 148 * per_sm ? blocks : 148 * per_sm;
         *n_launched = 2;     // tells the caller to launch hfa_launch_edge as well (on a forked stream)
