@@ -1141,6 +1141,7 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         if (tt0 == 0 && rows == TT) {
             // full tile: operands of the next frame (emissions, their f64 products, edge pair) are
             // fetched / converted while the current frame's chain runs; two frames per iteration
+            // (unrolling the whole tile measured slower: 0.157 vs 0.154 ms on config 2)
             uint32_t mbit = 1u;
 #pragma unroll 1
             for (int tt = 0; tt < TT; tt += 2) {
