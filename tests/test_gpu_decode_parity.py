@@ -423,3 +423,35 @@ def test_random_planted_batches_match_the_oracle_in_every_route(mix):
         idx, tim, _ = res.segments(b)
         assert np.array_equal(idx, r["ph_idx_seq"]) and np.array_equal(tim, r["ph_time_int"]), (mix, b)
     assert len(bad) <= n // 10, f"{len(bad)} of {n} paths differ from the oracle on peaked logits"
+
+
+def test_corpus_flow_sharded_and_chunked_equals_one_batch():
+    """BASELINE configs[4] in miniature: a corpus sharded over two (virtual) ranks by cost, every shard
+    streamed in chunks of bounded size, results merged in corpus order -- identical to aligning the
+    whole corpus as one batch (which takes a different kernel route)."""
+    from hubertfa_b200 import sharding
+    V = 39
+    T, S = synth.sample_shapes(360, seed=77, min_s=1, max_s=8, s_lo=3, s_hi=150)
+    vocab, items = synth.make_batch(T, S, V, seed=77, planted=True)
+    dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+    frames = [it["frame"].cuda() for it in items]
+    edges = [it["edge"].cuda() for it in items]
+    whole = dec.decode_batch(frames, edges, [it["ph_seq"] for it in items])
+    parts = []
+    for shard in sharding.shard_by_cost(T, S, 2):
+        segs = [None] * len(shard)
+        conf = [None] * len(shard)
+        for c in sharding.chunk_by_bytes(T[shard], S[shard], max_cells=1_500_000):
+            idx = shard[c]
+            r = dec.decode_batch([frames[i] for i in idx], [edges[i] for i in idx], [items[i]["ph_seq"] for i in idx])
+            for j, pos in enumerate(c):
+                segs[pos] = r.segments(j)
+                conf[pos] = r.total_confidence[j]
+        parts.append((shard, dict(segs=segs, conf=conf)))
+    merged = sharding._merge(parts)
+    assert len(merged["segs"]) == len(items) and all(s is not None for s in merged["segs"])
+    for b in range(len(items)):
+        idx, tim, iv = merged["segs"][b]
+        widx, wtim, wiv = whole.segments(b)
+        assert np.array_equal(idx, widx) and np.array_equal(tim, wtim) and np.array_equal(iv, wiv)
+        np.testing.assert_allclose(merged["conf"][b], whole.total_confidence[b], rtol=1e-5)
