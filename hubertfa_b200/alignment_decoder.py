@@ -174,25 +174,48 @@ class AlignmentDecoder:
         S = np.array([len(i) for i in ids_list], dtype=np.int32)
         ids = np.concatenate(ids_list).astype(np.int32) if len(ids_list) else np.zeros(0, np.int32)
         plan = ops.AlignPlan(T, S, ids, self.vocab["vocab_size"], self.frame_length)
+        # One device context and the C ABI called directly (the torch custom ops wrap the same entry
+        # points; their dispatcher costs ~50 us per call, which matters for the one-utterance-per-call
+        # pattern of predict_step).  Pinned result buffers are kept across calls (grow-only).
+        lib = _lib.load()
+        n = len(frames)
+        tabs = [np.fromiter((f.data_ptr() for f in frames), dtype=np.int64, count=n),
+                np.fromiter((f.stride(0) for f in frames), dtype=np.int64, count=n),
+                np.fromiter((f.stride(1) for f in frames), dtype=np.int64, count=n),
+                np.fromiter((e.data_ptr() for e in edges), dtype=np.int64, count=n),
+                np.fromiter((e.stride(0) for e in edges), dtype=np.int64, count=n)]
         with torch.cuda.device(dev):
             ws = plan.new_workspace(dev)
             res = plan.new_result(dev)
             fc = torch.empty(max(plan.total_frames, 1), dtype=torch.float32, device=dev) \
                 if want_frame_conf else None
-            plan.upload(ws)
-            plan.set_inputs(ws, [f.data_ptr() for f in frames], [f.stride(0) for f in frames],
-                            [f.stride(1) for f in frames], [e.data_ptr() for e in edges],
-                            [e.stride(0) for e in edges])
-            ops.align_batch(ws, plan.handle, ops.TORCH_TO_DTYPE[dtype], res, fc)
-            host = torch.empty(plan.result_bytes, dtype=torch.uint8, pin_memory=True)
+            stream = torch.cuda.current_stream()
+            sp, h, wp = int(stream.cuda_stream), plan.handle, ws.data_ptr()
+            _lib.check(lib.hfa_plan_upload(h, wp, sp), "hfa_plan_upload")
+            _lib.check(lib.hfa_set_inputs(h, wp, *[a.ctypes.data for a in tabs], sp), "hfa_set_inputs")
+            _lib.check(lib.hfa_align_batch(h, wp, ops.TORCH_TO_DTYPE[dtype], res.data_ptr(),
+                                           fc.data_ptr() if fc is not None else None, sp), "hfa_align_batch")
+            host = self._pinned("res", plan.result_bytes, torch.uint8)
             host.copy_(res, non_blocking=True)
             fc_host = None
             if fc is not None:
-                fc_host = torch.empty(fc.shape, dtype=torch.float32, pin_memory=True)
+                fc_host = self._pinned("fc", fc.numel(), torch.float32)
                 fc_host.copy_(fc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        views = plan.views(host.numpy())
-        return plan, views, (fc_host.numpy()[:plan.total_frames] if fc_host is not None else None), ws
+            stream.synchronize()
+        # the pinned buffers are reused by the next call: hand out copies
+        host = host.numpy().copy()
+        if fc_host is not None:
+            fc_host = fc_host.numpy().copy()
+        views = plan.views(host)
+        return plan, views, (fc_host[:plan.total_frames] if fc_host is not None else None), ws
+
+    def _pinned(self, key: str, numel: int, dtype) -> torch.Tensor:
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        buf = cache.get(key)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel * 1.5), 1024), dtype=dtype, pin_memory=True)
+            cache[key] = buf
+        return buf[:numel]
 
     # ----------------------------------------------------------------------------------------
     def decode(self,
