@@ -316,6 +316,8 @@ def main():
             step(i, stage_evs[i])
         torch.cuda.current_stream().wait_stream(d2h_stream)      # the last download is inside the region
         e1.record()
+        if clocks.nv is not None:
+            clocks._once()           # the queue is still draining: at least one sample under load even for tiny K
         torch.cuda.synchronize()
         clk = clocks.stop()
         launches = ops.launch_count() - launches0
