@@ -11,6 +11,8 @@
 #include <numeric>
 #include <vector>
 
+#include <cuda.h>      // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "../../include/hfa_align.h"
 #include "hfa_common.cuh"
 
@@ -58,6 +60,27 @@ int cuda_fail(cudaError_t e, const char *what)
 }
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// cuTensorMapEncodeTiled without linking libcuda: resolved once through the runtime
+typedef CUresult (*HfaEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+HfaEncodeTiled tensor_map_encoder()
+{
+    // HFA_NO_TENSORMAP=1 (read on every call, so tests can flip it): the band kernel's producer falls
+    // back to one 1-D bulk copy per frame row
+    if (const char *e = std::getenv("HFA_NO_TENSORMAP"))
+        if (e[0] == '1') return nullptr;
+    static const HfaEncodeTiled fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return (HfaEncodeTiled) nullptr;
+        return reinterpret_cast<HfaEncodeTiled>(f);
+    }();
+    return fn;
+}
 
 // side streams for the concurrent per-class DP launches: one set per (host thread, device)
 struct HfaSideStreams {
@@ -119,7 +142,8 @@ struct hfa_plan {
     // byte offsets
     int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
-            o_last = 0, o_dpst = 0, o_jump = 0, o_moves = 0, o_rowent = 0, o_band_items = 0, o_jblk_utt = 0, o_jblk_first = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, ws_bytes = 0;
+            o_last = 0, o_dpst = 0, o_jump = 0, o_moves = 0, o_rowent = 0, o_band_items = 0, o_jblk_utt = 0, o_jblk_first = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, o_tmaps = 0, ws_bytes = 0;
+    int32_t n_tmaps = 0;                       // banded utterances (one emission tensor map each)
     std::vector<unsigned char> head;           // host image of the head (without inputs)
     // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
     // aligned base pointers and positive row strides of at most this many elements (TMA path)
@@ -153,6 +177,7 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.row_entry = reinterpret_cast<int32_t *>(b + p->o_rowent);
     w.jblk_utt = reinterpret_cast<const int32_t *>(b + p->o_jblk_utt);
     w.jblk_first = reinterpret_cast<const int32_t *>(b + p->o_jblk_first);
+    w.tmaps = (p->n_tmaps > 0 && tensor_map_encoder() != nullptr) ? b + p->o_tmaps : nullptr;
     w.band_items = reinterpret_cast<const HfaBandItem *>(b + p->o_band_items);
     w.band_ticket = reinterpret_cast<int32_t *>(b + p->o_band_ticket);
     w.band_xchg = reinterpret_cast<uint4 *>(b + p->o_band_xchg);
@@ -239,6 +264,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             m.edge_off = edge;
             m.bp_off = words;
             m.dp_off = -1;
+            m.tmap = -1;
             p->frame_off[b] = frames;
             if (st == HFA_UTT_OK) {
                 m.T = t;
@@ -354,8 +380,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 // the banded routing is the latency regime: the forward pass also keeps dp (4 B per
                 // cell more HBM traffic, irrelevant there) so that the backtrace reads dp[t, s_t]
                 // instead of re-running the serial chain along the path
+                p->utt[b].band_k = k;
+                p->utt[b].tmap = p->n_tmaps++;
                 if (keep_dp) {
-                    p->utt[b].band_k = k;
                     p->utt[b].dp_off = p->dp_store_elems;
                     p->dp_store_elems += (int64_t)nb * p->utt[b].T * 32 * k;    // one [T][32 k] block per band
                 }
@@ -431,6 +458,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_moves = region(jump_tables ? words : 0);
         p->o_rowent = region(jump_tables ? edge / 16 * 4 : 0);
 
+        p->o_tmaps = region((int64_t)p->n_tmaps * 128);
         p->o_band_ticket = region(p->band_items.empty() ? 0 : 8);
         p->o_band_xchg = region(p->band_xchg_elems * 16);
         p->band_bytes = o - p->o_band_ticket;
@@ -550,6 +578,27 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
     cudaError_t e = cudaMemcpyAsync(workspace, p->head.data(), (size_t)p->head_bytes,
                                     cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload");
+    if (p->n_tmaps > 0 && tensor_map_encoder() != nullptr) {
+        // TMA tensor maps over emis[t][s] of the banded utterances (they hold the workspace address, so
+        // they are built here): rank 2, f32, dims {Sp, T}, row pitch Sp * 4 B, box {32 K, 16}
+        std::vector<CUtensorMap> maps((size_t)p->n_tmaps);
+        for (const HfaUtt &m : p->utt) {
+            if (m.status != 0 || m.tmap < 0) continue;
+            const cuuint64_t dims[2] = {(cuuint64_t)m.Sp, (cuuint64_t)m.T};
+            const cuuint64_t pitch[1] = {(cuuint64_t)m.Sp * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)(32 * m.band_k), (cuuint32_t)HFA_TILE_T};
+            const cuuint32_t estr[2] = {1, 1};
+            void *base = static_cast<unsigned char *>(workspace) + p->o_emis + m.emis_off * 4;
+            const CUresult r = tensor_map_encoder()(&maps[(size_t)m.tmap], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base,
+                                                    dims, pitch, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(HFA_ERR_CUDA, "hfa_plan_upload: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        }
+        e = cudaMemcpyAsync(static_cast<unsigned char *>(workspace) + p->o_tmaps, maps.data(), maps.size() * 128,
+                            cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload: tensor maps");
+    }
     if (p->band_bytes > 0) {       // band tickets + exchange slots start (and are left) all-zero
         e = cudaMemsetAsync(static_cast<unsigned char *>(workspace) + p->o_band_ticket, 0,
                             (size_t)p->band_bytes, static_cast<cudaStream_t>(stream));

@@ -32,7 +32,7 @@ struct HfaUtt {                  // 80 bytes, one per utterance, device copy liv
     int64_t dp_off;              // floats into dp_store when the forward pass keeps dp for this utterance
                                  // (banded routing; one [T][32 K] block per band, hfa_dp_store_index), else -1
     int32_t band_k;              // states per lane of that banded pass (2 / 4 / 8)
-    int32_t reserved;
+    int32_t tmap;                // index of the utterance's emission tensor map (banded routing), else -1
 };
 static_assert(sizeof(HfaUtt) == 80, "HfaUtt is 80 bytes (16-byte multiple)");
 
@@ -72,6 +72,9 @@ struct HfaWs {
     int32_t *row_entry;          // [sum ceil(T/16)] state of the best path at the last frame of each row
     const int32_t *jblk_utt;     // utterance of every 256-word block of the jump-table kernel
     const int32_t *jblk_first;   // [n_utt + 1] first such block of every utterance
+    // 128-byte TMA tensor maps (CUtensorMap) over emis[t][s] of the banded utterances: box = 16 frames
+    // x one band window; NULL when the driver entry point is unavailable (row copies are used then)
+    const void *tmaps;
     const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
     int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
     uint4 *band_xchg;            // {dp, tag, p.lo, tag}{p.hi, tag, 0, tag} of a band's last 32 states per tile;
@@ -133,6 +136,14 @@ __device__ __forceinline__ void hfa_bulk_commit() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void hfa_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void hfa_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void hfa_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 2-D tensor tile copy global -> shared (TMA, SASS UTMALDG): box position {x = column, y = row}
+__device__ __forceinline__ void hfa_tensor_load_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(hfa_smem_u32(dst_smem)), "l"(tmap), "r"(x), "r"(y), "r"(hfa_smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;

@@ -914,6 +914,8 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
             }
             if (lane == 0) issue_logits(0);
         }
+        const unsigned char *tmap = (ws.tmaps != nullptr && m.tmap >= 0)
+                                        ? static_cast<const unsigned char *>(ws.tmaps) + (size_t)m.tmap * 128 : nullptr;
         uint4 *left_x = ws.band_xchg + (has_left ? ws.band_items[item - 1].xoff : 0) + 2 * lane;
         // dp store: the compute warp leaves dp[t][.] of a tile in the stage it has just consumed (in
         // place of the emissions); before the stage is refilled the tile goes out as one bulk store.
@@ -1013,6 +1015,14 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                         for (int k = 0; k < K; ++k) o[d][k] = __fsub_rn(__fsub_rn(o[d][k], sv[d].x), sv[d].y);
                         if (r0 + d < rows) put_row(r0 + d, o[d]);
                     }
+                }
+            } else if (tmap != nullptr) {
+                // ONE tensor-tile copy per stage: box = 16 frames x W columns at {c0, t0} of emis[t][s]
+                // (rows past T and columns past Sp are zero-filled and never used)
+                if (lane == 0) {
+                    hfa_mbar_expect_tx(&full[st], (uint32_t)(TILE_FLOATS * 4) + TT * (uint32_t)sizeof(float2));
+                    hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &full[st]);
+                    hfa_tensor_load_2d(tile0 + st * TILE_FLOATS, tmap, c0, t0, &full[st]);
                 }
             } else {
                 if (lane == 0) {

@@ -99,8 +99,9 @@ int hfa_plan_algorithmic_bytes(const hfa_plan *plan, int32_t dtype, int64_t out[
  * forward pass keeps dp for the backtrace, out[7] reserved. */
 int hfa_plan_routing(const hfa_plan *plan, int32_t out[8]);
 
-/* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace and
- * zeroes the banded kernel's exchange table.
+/* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace, zeroes
+ * the banded kernel's exchange table and writes the TMA tensor maps of its emission windows (they
+ * hold addresses inside THIS workspace).
  * Must be enqueued once per (plan, workspace) before any compute call. */
 int hfa_plan_upload(const hfa_plan *plan, void *workspace /*[dev]*/, void *stream);
 

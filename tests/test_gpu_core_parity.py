@@ -11,14 +11,15 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "auto"],
+@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "2rc", "auto"],
                 ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
-                     "banded-no-dp-store", "auto"])
+                     "banded-no-dp-store", "banded-row-copies", "auto"])
 def routing(request, monkeypatch):
     """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
     S > 256 in the CTA kernel; 1 = utterances with > 64 states go to the multi-warp CTA kernel;
     2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane, the backtrace
-    reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path; auto = the plan's
+    reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path, or (row-copies)
+    without the TMA tensor maps; auto = the plan's
     own choice (banded with 2 states per lane for these small batches)."""
     if request.param != "auto":
         monkeypatch.setenv("HFA_LATENCY_MODE", request.param[0])
@@ -27,6 +28,8 @@ def routing(request, monkeypatch):
         monkeypatch.setenv("HFA_BIG_K", request.param[2])
     if request.param == "2nk":
         monkeypatch.setenv("HFA_KEEP_DP", "0")
+    if request.param == "2rc":                     # 1-D row copies instead of the TMA tensor-tile loads
+        monkeypatch.setenv("HFA_NO_TENSORMAP", "1")
     return request.param
 
 
