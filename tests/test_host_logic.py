@@ -175,3 +175,46 @@ def test_gather_on_host_world_size_2_gloo():
     T, S = synth.sample_shapes(40, seed=9)
     assert n_seg == [int(s) for s in S]
     assert all(t.startswith(f"utt{i}@") for i, t in enumerate(tag))
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """include/hfa_align.h must be usable from C (the drop-in boundary is a C ABI): compile a C
+    translation unit with gcc -std=c99 -pedantic against it, link libhfa_align.so, run the host-only
+    entry points (collation of a ragged batch) -- no GPU involved."""
+    import os
+    import shutil
+    import subprocess
+    from hubertfa_b200 import LIB_PATH
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "hfa_align.h"
+int main(void) {
+    const int32_t T[3] = {500, 0, 40}, S[3] = {40, 3, 5};
+    int32_t ids[48] = {0};
+    hfa_plan *plan = 0;
+    HfaResultLayout lay;
+    int32_t routing[8];
+    if (hfa_abi_version() != HFA_ABI_VERSION) return 1;
+    if (hfa_plan_create(3, 63, T, S, ids, 0.02, &plan) != HFA_OK) { puts(hfa_last_error()); return 2; }
+    if (hfa_plan_total_cells(plan) != 500 * 40 + 40 * 5) return 3;
+    if (hfa_plan_result_layout(plan, &lay) != HFA_OK || lay.total_bytes <= 0) return 4;
+    if (hfa_plan_routing(plan, routing) != HFA_OK) return 5;
+    {
+        hfa_plan *bad = 0;
+        if (hfa_plan_create(1, 0, T, S, ids, 0.02, &bad) != HFA_ERR_ARG || bad != 0) return 6;   /* bad vocabulary size */
+    }
+    printf("workspace bytes = %lld\n", (long long)hfa_plan_workspace_bytes(plan));
+    hfa_plan_destroy(plan);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-l:libhfa_align.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
