@@ -56,6 +56,7 @@ SYMBOLS = {
     "hfa_forward_fused": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hfa_plan_algorithmic_bytes_fused": (_i64, [_vp, _i32]),
     "hfa_debug_unpack_backptr": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "hfa_debug_unpack_dp": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "hfa_ctc_greedy": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -26,6 +26,8 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
                               float *dp_dump);
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
                                bool keep_dp, int64_t fused_row_stride, float *dp_dump);
+cudaError_t hfa_launch_dp_skew(const HfaLaunchCtx &c, int d, int item_begin, int n_items, int32_t *ticket,
+                               bool keep_dp, float *dp_dump);
 cudaError_t hfa_launch_emission(const HfaLaunchCtx &c, int total_row_blocks, int max_sp, int dtype,
                                 int64_t max_row_stride, int *n_launched);
 cudaError_t hfa_launch_edge(const HfaLaunchCtx &c, int total_row_blocks, int dtype);
@@ -35,6 +37,7 @@ cudaError_t hfa_launch_pack(const HfaLaunchCtx &c, int total_row_blocks, const f
 cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
                                  const HfaResultPtrs &res, float *frame_conf, float *dp_path);
 cudaError_t hfa_launch_unpack_bp(const HfaLaunchCtx &c, int utt, int8_t *out);
+cudaError_t hfa_launch_unpack_dp(const HfaLaunchCtx &c, int utt, float *out);
 cudaError_t hfa_launch_ctc_greedy(const void *logits, int dtype, int T, int V, int64_t st_t, int64_t st_v,
                                   int32_t *arg, int32_t *out_ids, int32_t *out_len, cudaStream_t stream);
 cudaError_t hfa_launch_jump_tables(const HfaLaunchCtx &c, int n_blocks);
@@ -131,6 +134,9 @@ struct hfa_plan {
     // 2 states per lane), [1] long phoneme sequences (S > 256, band_k[1] states per lane)
     std::vector<HfaBandItem> band_items;
     int32_t band_begin[2] = {0, 0}, band_count[2] = {0, 0}, band_k[2] = {2, 4};
+    // > 0: the list runs in the skewed-wavefront kernel (hfa_dp_skew.cu) with this many frames of skew
+    // per state -- 32 / 30-state strips, one state per lane -- instead of the halo bands
+    int32_t band_skew[2] = {0, 0};
     int64_t band_xchg_elems = 0, dp_store_elems = 0;
     std::vector<int32_t> jblk_utt, jblk_first; // jump-table kernel: 256-word blocks per utterance
     int32_t n_valid = 0, n_kept = 0;           // valid utterances / utterances that keep dp
@@ -314,7 +320,14 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         //   HFA_LATENCY_MODE = 0: never band (S <= 256) | 2: always band | 1: the older multi-warp
         //   CTA kernel with a barrier per frame | unset: band when the batch has <= HFA_BAND_MAX
         //   (default 1184 = 8 per SM) band warps.   HFA_BIG_KERNEL = cta | band, HFA_BIG_K = 2|4|8.
+        // Latency-regime kernel: the skewed wavefront (default; needs the TMA tensor maps) or the halo bands.
+        //   HFA_LAT_KERNEL = skew | band,   HFA_SKEW_D = 2 | 3 (frames of skew per state)
+        int skew_d = 2;
+        if (const char *e = std::getenv("HFA_SKEW_D")) skew_d = (std::atoi(e) == 3) ? 3 : 2;
+        if (const char *e = std::getenv("HFA_LAT_KERNEL")) { if (e[0] == 'b') skew_d = 0; }
+        if (tensor_map_encoder() == nullptr) skew_d = 0;
         auto n_bands = [&](int32_t b, int k) {
+            if (k == 1) return hfa_skew_strips(p->utt[b].Sp);
             const int w = 32 * k, own = w - 32, sp = p->utt[b].Sp;
             return sp <= w ? 1 : (sp - 32 + own - 1) / own;
         };
@@ -334,7 +347,11 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         } else if (lat_mode != 0) {
             int64_t nb = 0;
             for (int c = 0; c < HFA_NUM_CLASSES; ++c)
-                for (int32_t b : lists[c]) nb += n_bands(b, 2);
+                for (int32_t b : lists[c]) nb += n_bands(b, skew_d > 0 ? 1 : 2);
+            if (skew_d > 0) {
+                p->band_k[0] = 1;
+                p->band_skew[0] = skew_d;
+            }
             if (lat_mode == 2 || (nb > 0 && nb <= band_max)) {
                 for (int c = 0; c < HFA_NUM_CLASSES; ++c) {
                     lat_band.insert(lat_band.end(), lists[c].begin(), lists[c].end());
@@ -361,8 +378,10 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 big_k = 8;
                 for (int k : {2, 4, 8})
                     if (count(k) <= band_max) { big_k = k; break; }
+                if (skew_d > 0 && count(1) <= band_max) big_k = 1;      // strips of the skewed kernel
             }
             p->band_k[1] = big_k;
+            if (big_k == 1) p->band_skew[1] = skew_d;
             if (big_mode == 1 || (big_mode == -1 && count(big_k) <= band_max)) {
                 big_band = lists[HFA_NUM_CLASSES];
                 lists[HFA_NUM_CLASSES].clear();
@@ -373,10 +392,12 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         if (const char *e = std::getenv("HFA_KEEP_DP")) keep_dp = (e[0] != '0');
         auto add_bands = [&](const std::vector<int32_t> &utts, int which) {
             const int k = p->band_k[which];
+            const int sd = p->band_skew[which];
             p->band_begin[which] = (int32_t)p->band_items.size();
             for (int32_t b : utts) {
                 const int nb = n_bands(b, k);
                 const int64_t tiles = (p->utt[b].T + 15) / 16;
+                p->utt[b].skew_d = sd;
                 // the banded routing is the latency regime: the forward pass also keeps dp (4 B per
                 // cell more HBM traffic, irrelevant there) so that the backtrace reads dp[t, s_t]
                 // instead of re-running the serial chain along the path
@@ -384,12 +405,15 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 p->utt[b].tmap = p->n_tmaps++;
                 if (keep_dp) {
                     p->utt[b].dp_off = p->dp_store_elems;
-                    p->dp_store_elems += (int64_t)nb * p->utt[b].T * 32 * k;    // one [T][32 k] block per band
+                    // bands: one [T][32 k] block per band; strips: one 128-byte row per iteration
+                    p->dp_store_elems += sd > 0 ? (int64_t)nb * hfa_skew_blocks(sd, p->utt[b].T) * 512
+                                                : (int64_t)nb * p->utt[b].T * 32 * k;
                 }
                 for (int j = 0; j < nb; ++j) {
                     const bool has_right = j + 1 < nb;
                     p->band_items.push_back(HfaBandItem{b, j, has_right ? p->band_xchg_elems : 0});
-                    if (has_right) p->band_xchg_elems += tiles * 64;
+                    // exchange slots (16 bytes each): bands 32 states x 2 per tile, strips one per frame
+                    if (has_right) p->band_xchg_elems += sd > 0 ? tiles * 16 : tiles * 64;
                 }
             }
             p->band_count[which] = (int32_t)p->band_items.size() - p->band_begin[which];
@@ -552,7 +576,7 @@ int hfa_plan_routing(const hfa_plan *p, int32_t out[8])
     out[4] = p->band_k[1];
     out[5] = p->lat_count + p->class_count[HFA_NUM_CLASSES];
     out[6] = p->dp_store_elems > 0;
-    out[7] = 0;
+    out[7] = std::max(p->band_skew[0], p->band_skew[1]);
     return HFA_OK;
 }
 
@@ -586,7 +610,7 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
             if (m.status != 0 || m.tmap < 0) continue;
             const cuuint64_t dims[2] = {(cuuint64_t)m.Sp, (cuuint64_t)m.T};
             const cuuint64_t pitch[1] = {(cuuint64_t)m.Sp * 4};
-            const cuuint32_t box[2] = {(cuuint32_t)(32 * m.band_k), (cuuint32_t)HFA_TILE_T};
+            const cuuint32_t box[2] = {(cuuint32_t)(m.skew_d > 0 ? HFA_SKEW_BOX : 32 * m.band_k), (cuuint32_t)HFA_TILE_T};
             const cuuint32_t estr[2] = {1, 1};
             void *base = static_cast<unsigned char *>(workspace) + p->o_emis + m.emis_off * 4;
             const CUresult r = tensor_map_encoder()(&maps[(size_t)m.tmap], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base,
@@ -755,12 +779,15 @@ static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_du
             e = hfa_launch_dp_warp_any(c, p->warp_max_k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k > 0)
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
-        else if (items[it].k == -3)
-            e = hfa_launch_dp_band(c, p->band_k[0], p->band_begin[0], p->band_count[0], c.ws.band_ticket,
-                                   p->dp_store_elems > 0, fused_row_stride, dp_dump);
-        else if (items[it].k == -4)
-            e = hfa_launch_dp_band(c, p->band_k[1], p->band_begin[1], p->band_count[1],
-                                   c.ws.band_ticket + 1, p->dp_store_elems > 0, fused_row_stride, dp_dump);
+        else if (items[it].k == -3 || items[it].k == -4) {
+            const int wh = items[it].k == -3 ? 0 : 1;
+            if (p->band_skew[wh] > 0)
+                e = hfa_launch_dp_skew(c, p->band_skew[wh], p->band_begin[wh], p->band_count[wh],
+                                       c.ws.band_ticket + wh, p->dp_store_elems > 0, dp_dump);
+            else
+                e = hfa_launch_dp_band(c, p->band_k[wh], p->band_begin[wh], p->band_count[wh],
+                                       c.ws.band_ticket + wh, p->dp_store_elems > 0, fused_row_stride, dp_dump);
+        }
         else if (items[it].k == -2)
             e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else
@@ -809,7 +836,8 @@ static bool fused_ok(const hfa_plan *p, int32_t dtype)
 {
     const bool all_banded = p->warp_all_count == 0 && p->lat_count == 0 &&
                             p->class_count[HFA_NUM_CLASSES] == 0 && !p->band_items.empty();
-    return all_banded && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && p->max_row_stride > 0 &&
+    const bool skewed = p->band_skew[0] > 0 || p->band_skew[1] > 0;   // no producer warp there to fuse into
+    return all_banded && !skewed && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && p->max_row_stride > 0 &&
            p->vocab <= 256 && p->max_row_stride * 4 * HFA_TILE_T <= 48 * 1024;
 }
 
@@ -887,6 +915,20 @@ int hfa_debug_unpack_backptr(const hfa_plan *p, const void *workspace, int32_t u
     HfaLaunchCtx c = make_ctx(p, const_cast<void *>(workspace), stream);
     cudaError_t e = hfa_launch_unpack_bp(c, utt, out);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_debug_unpack_backptr: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+int hfa_debug_unpack_dp(const hfa_plan *p, const void *workspace, int32_t utt, float *out, void *stream)
+{
+    if (!p || !workspace || !out) return fail(HFA_ERR_ARG, "hfa_debug_unpack_dp: NULL argument");
+    if (utt < 0 || utt >= p->n_utt || p->utt[utt].status != 0)
+        return fail(HFA_ERR_ARG, "hfa_debug_unpack_dp: bad utterance %d", utt);
+    if (p->utt[utt].dp_off < 0)
+        return fail(HFA_ERR_UNSUPPORTED, "hfa_debug_unpack_dp: the forward pass keeps no dp for utterance %d", utt);
+    HfaLaunchCtx c = make_ctx(p, const_cast<void *>(workspace), stream);
+    cudaError_t e = hfa_launch_unpack_dp(c, utt, out);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_debug_unpack_dp: launch");
     g_launches += 1;
     return HFA_OK;
 }

@@ -474,7 +474,8 @@ hfa_backtrace_tables_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, 
 #pragma unroll
             for (int f = 0; f < 16; ++f) {
                 const int t = min(16 * wr + f, T - 1);
-                dv[f] = dps[hfa_dp_store_index(m.band_k, T, t, path_state[t])];
+                dv[f] = dps[m.skew_d > 0 ? hfa_skew_dp_index(m.skew_d, T, t, path_state[t])
+                                         : hfa_dp_store_index(m.band_k, T, t, path_state[t])];
             }
 #pragma unroll
             for (int f = 0; f < 16; ++f)
@@ -534,7 +535,26 @@ __global__ void hfa_unpack_bp_kernel(HfaWs ws, int u, int8_t *__restrict__ out)
     }
 }
 
+// test helper: the dp the forward pass kept for one utterance (latency plans), as f32 [T][S]
+__global__ void hfa_unpack_dp_kernel(HfaWs ws, int u, float *__restrict__ out)
+{
+    const HfaUtt m = ws.utt[u];
+    const float *dps = ws.dp_store + m.dp_off;
+    const int64_t n = (int64_t)m.T * m.S;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / m.S), s = (int)(i - (int64_t)t * m.S);
+        out[i] = dps[m.skew_d > 0 ? hfa_skew_dp_index(m.skew_d, m.T, t, s) : hfa_dp_store_index(m.band_k, m.T, t, s)];
+    }
+}
+
 }  // namespace
+
+cudaError_t hfa_launch_unpack_dp(const HfaLaunchCtx &c, int utt, float *out)
+{
+    hfa_unpack_dp_kernel<<<148, 256, 0, c.stream>>>(c.ws, utt, out);
+    return cudaGetLastError();
+}
 
 cudaError_t hfa_launch_backtrace(const HfaLaunchCtx &c, const int32_t *order, int n,
                                  const HfaResultPtrs &res, float *frame_conf, float *dp_path)

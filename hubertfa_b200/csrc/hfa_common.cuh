@@ -21,7 +21,7 @@
 #define HFA_CTA_K 8              // states per thread in the CTA-per-utterance kernel
 #define HFA_NUM_CLASSES 8        // K = 1..8 for the warp kernel (index K-1); class 8 -> CTA kernel
 
-struct HfaUtt {                  // 80 bytes, one per utterance, device copy lives in the workspace
+struct HfaUtt {                  // 96 bytes, one per utterance, device copy lives in the workspace
     int32_t T, S, Sp, status;
     int64_t seg_off;             // into ids / per-segment outputs (ints)
     int64_t emis_off;            // floats, multiple of 4
@@ -31,10 +31,13 @@ struct HfaUtt {                  // 80 bytes, one per utterance, device copy liv
     int64_t cell_off;            // sum of T*S of the previous utterances (dense ragged dumps)
     int64_t dp_off;              // floats into dp_store when the forward pass keeps dp for this utterance
                                  // (banded routing; one [T][32 K] block per band, hfa_dp_store_index), else -1
-    int32_t band_k;              // states per lane of that banded pass (2 / 4 / 8)
-    int32_t tmap;                // index of the utterance's emission tensor map (banded routing), else -1
+    int32_t band_k;              // states per lane of that banded pass (2 / 4 / 8; 1 = skewed kernel)
+    int32_t tmap;                // index of the utterance's emission tensor map (banded / skewed routing), else -1
+    int32_t skew_d;              // > 0: the skewed-wavefront kernel ran this utterance with this many frames of
+                                 // skew per state; its kept dp uses the skewed layout (hfa_skew_dp_index)
+    int32_t pad_[3];
 };
-static_assert(sizeof(HfaUtt) == 80, "HfaUtt is 80 bytes (16-byte multiple)");
+static_assert(sizeof(HfaUtt) == 96, "HfaUtt is 96 bytes (16-byte multiple)");
 
 struct HfaInput {                // per-utterance logits descriptor (changes per call)
     const void *frame;
@@ -91,6 +94,27 @@ __host__ __device__ __forceinline__ int64_t hfa_dp_store_index(int K, int T, int
     const int W = 32 * K, OWN = W - 32;
     const int b = (s < W) ? 0 : 1 + (s - W) / OWN;
     return ((int64_t)b * T + t) * W + (s - b * OWN);
+}
+
+// Skewed-wavefront kernel (hfa_dp_skew.cu): one warp = one STRIP of the state axis, one state per lane.
+// Strip 0 covers states 0..31; strip w > 0 starts at column 30 w: its lanes 0 and 1 are GHOSTS that replay the
+// advance scores of the left strip's last two states, lanes 2..31 own states 30 w + 2 .. 30 w + 31.
+#define HFA_SKEW_OWN 30
+#define HFA_SKEW_BOX 36          // columns of its TMA box: the box starts at (30 w) & ~3, a 16-byte boundary
+__host__ __device__ __forceinline__ int hfa_skew_strips(int Sp)
+{
+    return Sp <= 32 ? 1 : 1 + (Sp - 32 + HFA_SKEW_OWN - 1) / HFA_SKEW_OWN;
+}
+// 16-iteration blocks a strip runs: lane p handles frame t at iteration t + p D, the last lane finishes
+// frame T-1 at iteration T - 1 + 31 D
+__host__ __device__ __forceinline__ int hfa_skew_blocks(int D, int T) { return (T + 31 * D + 15) >> 4; }
+// The kept dp of a skewed pass: every strip stores what its 32 lanes hold after each iteration, one
+// 128-byte row per iteration (so dp[t][s] sits at row t + p D of its strip, p = lane of state s).
+__host__ __device__ __forceinline__ int64_t hfa_skew_dp_index(int D, int T, int t, int s)
+{
+    const int w = (s < 32) ? 0 : 1 + (s - 32) / HFA_SKEW_OWN;
+    const int p = s - HFA_SKEW_OWN * w;
+    return ((int64_t)w * hfa_skew_blocks(D, T) * 16 + t + p * D) * 32 + p;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ __device__ __forceinline__ void hfa_select(const float (&e)[K], const float (&st
             "selp.f32 h, %7, h, q3;\n\t"
             "and.b32 %1, h, %8;\n\t"
             "}"
-            : "=f"(dp[k]), "+f"(cu[k]), "+r"(bits[k])
+            : "=&f"(dp[k]), "+f"(cu[k]), "+r"(bits[k])
             : "f"(p2), "f"(stay[k]), "f"(p3), "f"(jump_cap[k]), "f"(e[k]), "r"(sp_and[k]), "r"(m1),
               "r"(m2));
     }
@@ -230,7 +230,7 @@ __device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&
             "and.b32 hi, hi, %8;\n\t"
             "mov.b64 %1, {lo, hi};\n\t"
             "}"
-            : "=f"(dp[k]), "+d"(p[k]), "+r"(bits[k])
+            : "=&f"(dp[k]), "+d"(p[k]), "+r"(bits[k])
             : "f"(p2), "f"(stay[k]), "f"(p3), "f"(jump_cap[k]), "d"(pe[k]), "r"(sp_hi[k]), "r"(m1),
               "r"(m2));
     }

@@ -71,7 +71,7 @@ class AlignPlan:
         out = (C.c_int32 * 8)()
         check(self._lib.hfa_plan_routing(self._h, C.byref(out)))
         return dict(warp_utts=out[0], band_warps=out[1], band_k=out[2], big_band_warps=out[3],
-                    big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]))
+                    big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]), skew_d=out[7])
 
     def algorithmic_bytes_fused(self, dtype: int = _lib.DTYPE_F32) -> int:
         return int(self._lib.hfa_plan_algorithmic_bytes_fused(self._h, dtype))
@@ -206,6 +206,15 @@ def unpack_backptr(plan: AlignPlan, workspace: torch.Tensor, utt: int) -> torch.
     with torch.cuda.device(workspace.device):
         check(_lib.load().hfa_debug_unpack_backptr(plan.handle, workspace.data_ptr(), utt, out.data_ptr(),
                                                    _stream_ptr()), "hfa_debug_unpack_backptr")
+    return out
+
+
+def unpack_kept_dp(plan: AlignPlan, workspace: torch.Tensor, utt: int) -> torch.Tensor:
+    """Test helper: f32 [T, S] dp cells the (production) forward pass kept for the table backtrace."""
+    out = torch.empty((int(plan.T[utt]), int(plan.S[utt])), dtype=torch.float32, device=workspace.device)
+    with torch.cuda.device(workspace.device):
+        check(_lib.load().hfa_debug_unpack_dp(plan.handle, workspace.data_ptr(), utt, out.data_ptr(),
+                                              _stream_ptr()), "hfa_debug_unpack_dp")
     return out
 
 

@@ -96,7 +96,8 @@ int hfa_plan_algorithmic_bytes(const hfa_plan *plan, int32_t dtype, int64_t out[
  * out[0] utterances in the one-warp-per-utterance kernel, out[1] warps (bands) and out[2] states per
  * lane of the banded kernel for S <= 256 (small batches: several warps per utterance), out[3] / out[4]
  * the same for S > 256, out[5] utterances in the CTA-per-utterance kernels, out[6] 1 if the banded
- * forward pass keeps dp for the backtrace, out[7] reserved. */
+ * forward pass keeps dp for the backtrace, out[7] > 0: those lists run in the skewed-wavefront kernel
+ * (one state per lane, out[2] / out[4] == 1) with that many frames of skew per state. */
 int hfa_plan_routing(const hfa_plan *plan, int32_t out[8]);
 
 /* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace, zeroes
@@ -166,6 +167,11 @@ int hfa_ctc_greedy(const void *logits, int32_t dtype, int64_t T, int64_t V, int6
 /* out: [dev] int8 [T_b][S_b], codes 0/1/2 (row 0 is -1 like the reference, :247). */
 int hfa_debug_unpack_backptr(const hfa_plan *plan, const void *workspace, int32_t utt, int8_t *out,
                              void *stream);
+
+/* out: [dev] f32 [T_b][S_b]: the dp cells the forward pass KEPT for the table backtrace (latency plans,
+ * hfa_plan_routing out[6]) -- the production kernels' own values, unlike hfa_viterbi_forward's dp_dump.
+ * HFA_ERR_UNSUPPORTED when the plan keeps no dp for this utterance. */
+int hfa_debug_unpack_dp(const hfa_plan *plan, const void *workspace, int32_t utt, float *out, void *stream);
 
 /* byte offset of a workspace region (tests peek at intermediate buffers through this):
  * which = 0 emissions f32 [sum T*Sp] (Sp = S rounded up to 4), 1 edge pairs f32x2 (per utterance

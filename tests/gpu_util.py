@@ -28,6 +28,20 @@ def run_core_gpu(ids_list, prob_logs, els, nes, ps=None, frame_length=0.02, voca
     ops.pack_emissions(ws, plan.handle, pl, el, ne, pp)
     dp_dump = torch.full((max(plan.total_cells, 1),), float("nan"), dtype=torch.float32, device=dev) if dump else None
     ops.viterbi_forward(ws, plan.handle, dp_dump)
+    bt_dump = None
+    if dump:
+        # the dump run used the DUMP instantiations of the kernels; keep its backpointers, then run the
+        # PRODUCTION instantiation (what decode_batch launches) over the same workspace: its backpointer
+        # words and -- where the plan keeps dp -- its dp cells are compared with the oracle as well
+        torch.cuda.synchronize()
+        bt_dump = []
+        for b in range(plan.n_utt):
+            try:
+                bt_dump.append(ops.unpack_backptr(plan, ws, b).cpu().numpy())
+            except ops.HfaError:                      # invalid utterance: no backpointers
+                bt_dump.append(None)
+        plan.debug_region(ws, "bp").fill_(-1)
+        ops.viterbi_forward(ws, plan.handle, None)
     fc = torch.empty(max(plan.total_frames, 1), dtype=torch.float32, device=dev)
     dpp = torch.empty(max(plan.total_frames, 1), dtype=torch.float32, device=dev)
     ops.backtrace(ws, plan.handle, res, fc, dpp)
@@ -47,7 +61,10 @@ def run_core_gpu(ids_list, prob_logs, els, nes, ps=None, frame_length=0.02, voca
             n = T[b] * S[b]
             d["dp"] = dump_h[cell:cell + n].reshape(T[b], S[b])
             cell += n
-            d["bt"] = ops.unpack_backptr(plan, ws, b).cpu().numpy()
+            d["bt"] = bt_dump[b]
+            d["bt_prod"] = ops.unpack_backptr(plan, ws, b).cpu().numpy()
+            if plan.routing()["keeps_dp"]:
+                d["dp_kept"] = ops.unpack_kept_dp(plan, ws, b).cpu().numpy()
         out.append(d)
     return out
 
@@ -66,6 +83,9 @@ def check_core_against_oracle(ids, prob_log, el, ne, g, p=None, frame_length=0.0
         assert np.array_equal(bits(g["dp"]), bits(r["dp"]))
         assert np.array_equal(g["bt"][1:], r["bt"][1:])
         assert (g["bt"][0] == -1).all()
+        assert np.array_equal(g["bt_prod"][1:], r["bt"][1:]), "production kernel: backpointers differ"
+        if "dp_kept" in g:
+            assert np.array_equal(bits(g["dp_kept"]), bits(r["dp"])), "production kernel: kept dp differs"
     fc, tot = oc.confidence(r["dp_path"])
     fin = np.isfinite(fc)
     np.testing.assert_allclose(g["frame_conf"][fin], fc[fin], rtol=2e-6, atol=1e-30)

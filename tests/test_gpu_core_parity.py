@@ -11,22 +11,29 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "2rc", "auto"],
+@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "2rc", "2s2", "2s3", "2s2slow", "2s2nk", "auto"],
                 ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
-                     "banded-no-dp-store", "banded-row-copies", "auto"])
+                     "banded-no-dp-store", "banded-row-copies", "skew-d2", "skew-d3", "skew-d2-guarded-body",
+                     "skew-d2-no-dp-store", "auto"])
 def routing(request, monkeypatch):
     """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
     S > 256 in the CTA kernel; 1 = utterances with > 64 states go to the multi-warp CTA kernel;
     2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane, the backtrace
     reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path, or (row-copies)
-    without the TMA tensor maps; auto = the plan's
-    own choice (banded with 2 states per lane for these small batches)."""
+    without the TMA tensor maps; skew-* = everything (S > 256 included) in the skewed-wavefront kernel
+    with 2 / 3 frames of skew per state, through its unrolled steady-state body or (guarded-body) only
+    the guarded one; auto = the plan's own choice (the skewed kernel for these small batches)."""
     if request.param != "auto":
         monkeypatch.setenv("HFA_LATENCY_MODE", request.param[0])
         monkeypatch.setenv("HFA_BIG_KERNEL", "band" if request.param[0] == "2" else "cta")
+        monkeypatch.setenv("HFA_LAT_KERNEL", "skew" if request.param.startswith("2s") else "band")
     if request.param in ("2k4", "2k8"):
         monkeypatch.setenv("HFA_BIG_K", request.param[2])
-    if request.param == "2nk":
+    if request.param.startswith("2s"):
+        monkeypatch.setenv("HFA_SKEW_D", request.param[2])
+    if request.param == "2s2slow":
+        monkeypatch.setenv("HFA_SKEW_SLOW", "1")
+    if request.param in ("2nk", "2s2nk"):
         monkeypatch.setenv("HFA_KEEP_DP", "0")
     if request.param == "2rc":                     # 1-D row copies instead of the TMA tensor-tile loads
         monkeypatch.setenv("HFA_NO_TENSORMAP", "1")
@@ -135,13 +142,17 @@ def test_invalid_utterances_get_a_status():
     assert np.array_equal(v["ph_idx_seq"][:v["n_seg"][0]], r["ph_idx_seq"])
 
 
-@pytest.mark.parametrize("big", ["cta", "band2", "band4", "band8"])
+@pytest.mark.parametrize("big", ["cta", "band2", "band4", "band8", "skew2", "skew3"])
 def test_long_form_c3_stress(big, monkeypatch):
     """BASELINE config 3: one 10-minute utterance, T=30000, S=2000 (1875 word rows): the CTA-per-
-    utterance kernel and the banded kernel with 2 / 4 / 8 states per lane (63 / 21 / 9 warps)."""
+    utterance kernel, the banded kernel with 2 / 4 / 8 states per lane (63 / 21 / 9 warps) and the
+    skewed-wavefront kernel (67 strips) with 2 / 3 frames of skew per state."""
     monkeypatch.setenv("HFA_BIG_KERNEL", "cta" if big == "cta" else "band")
-    if big != "cta":
+    monkeypatch.setenv("HFA_LAT_KERNEL", "skew" if big.startswith("skew") else "band")
+    if big.startswith("band"):
         monkeypatch.setenv("HFA_BIG_K", big[4:])
+    if big.startswith("skew"):
+        monkeypatch.setenv("HFA_SKEW_D", big[4:])
     x = synth_core_inputs(30000, 2000, 63, 31337, "dictionary", planted=True)
     out = run_core_gpu([x["ids"]], [x["prob_log"]], [x["el"]], [x["ne"]], [x["p"]], dump=False)
     r = check_core_against_oracle(x["ids"], x["prob_log"], x["el"], x["ne"], out[0], x["p"], full=False)

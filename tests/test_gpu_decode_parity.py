@@ -278,12 +278,13 @@ def test_host_pipeline_matches_decode_batch():
                 assert bits(out["total_conf"][b]) == bits(ref.total_confidence[b])
 
 
-def test_fused_forward_equals_three_stage_route():
-    """Small batches: hfa_forward_fused (emissions computed by the DP kernel's producer warps, never
+def test_fused_forward_equals_three_stage_route(monkeypatch):
+    """Small batches, halo-band routing (HFA_LAT_KERNEL=band): hfa_forward_fused (emissions computed by the DP kernel's producer warps, never
     written to HBM) must give the same bits as hfa_emission + hfa_viterbi_forward -- backpointers,
     kept dp, results -- for strided [T, V+2] head views, all band widths, S up to 1030."""
     import torch
     from hubertfa_b200 import _lib, ops, synth
+    monkeypatch.setenv("HFA_LAT_KERNEL", "band")
     V = 63
     T = np.array([500, 130, 257, 700, 16, 17, 1, 333, 900, 1300], dtype=np.int32)
     S = np.array([40, 7, 65, 150, 5, 33, 3, 97, 256, 1030], dtype=np.int32)
@@ -365,12 +366,14 @@ def test_ctc_greedy_kernel_matches_numpy():
         assert np.array_equal(ops.ctc_greedy(x.cuda()).cpu().numpy(), onp.ctc_greedy(x.float().numpy()))
 
 
+@pytest.mark.parametrize("lat_kernel", ["skew", "band"])
 @pytest.mark.parametrize("mix", ["unsplit-fused", "split-bands", "with-long-sequences"])
-def test_random_planted_batches_match_the_oracle_in_every_route(mix):
+def test_random_planted_batches_match_the_oracle_in_every_route(mix, lat_kernel, monkeypatch):
     """decode_batch (auto routing) on many small random utterances with peaked (planted) logits,
     head-layout strided views: paths, end states and intervals must equal the C oracle run on the
     same logits.  The three mixes exercise the fused forward pass (no utterance split), the
     multi-band route and the route with S > 256 bands."""
+    monkeypatch.setenv("HFA_LAT_KERNEL", lat_kernel)
     rng = np.random.default_rng({"unsplit-fused": 1, "split-bands": 2, "with-long-sequences": 3}[mix])
     n = 120
     if mix == "unsplit-fused":
