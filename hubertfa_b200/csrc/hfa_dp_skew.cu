@@ -120,6 +120,19 @@ __device__ __forceinline__ void sk_bulk_store(void *dst, uint32_t src, uint32_t 
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
+// one lane of a converged warp (ptxas then emits the TMA / bulk instructions once, without an ELECT loop)
+__device__ __forceinline__ bool sk_elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void sk_bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // exchange slot of one frame: {adv31 bits | tag << 32, adv30 bits | tag << 32}
@@ -213,8 +226,8 @@ template <int NSTG> struct SkSmem {
     static constexpr uint32_t EDGE = TILE + (NSTG + 1) * SK_STG_B;        // [(NSTG + 1) x 16] float2
     static constexpr uint32_t DPST = EDGE + (NSTG + 1) * 16 * 8;          // 2 x [16][32] f32: kept-dp staging
     static constexpr uint32_t FEED = DPST + 2 * 2048;                     // [32][36] f32: ghost feeds, rows like a tile
-    static constexpr uint32_t PUB = FEED + 32 * SK_ROW_B;                 // adv31 [16], adv30 [16], scratch [48]
-    static constexpr uint32_t FULL = PUB + 80 * 4;                        // NSTG mbarriers
+    static constexpr uint32_t PUB = FEED + 32 * SK_ROW_B;                 // 2 x {adv31 [16], adv30 [16], scratch [48]}
+    static constexpr uint32_t FULL = PUB + 2 * 80 * 4;                    // NSTG mbarriers
     static constexpr uint32_t SLOT = FULL + NSTG * 8;                     // work-item ticket
     static constexpr uint32_t BYTES = SLOT + 16;
 };
@@ -274,8 +287,8 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     const bool seeded = !ghost && (s == 0 || (s == 1 && lead_sp));
     const float cap1 = (s == 0) ? NEG : POS;                   // nothing to the left of state 0
 
-    auto issue = [&](int i) {                                  // lane 0 only: tile i -> stage i % NSTG
-        const int st = i % NSTG;
+    // tile i -> stage st (= i % NSTG, kept as a running counter); executed by ONE elected lane
+    auto issue = [&](int i, int st) {
         const int t0 = i * 16;
         const uint32_t bar = sm0 + SM::FULL + 8u * (uint32_t)st;
         if (t0 >= T) {                                         // nothing to fetch: complete the phase
@@ -291,8 +304,12 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
             sk_bulk_load(sm0 + SM::EDGE + (uint32_t)NSTG * 128u, g_edge + t0, 128u, bar);
         }
     };
-    if (lane == 0)
-        for (int i = 0; i < PF && i < NB; ++i) issue(i);
+    static_assert(PF + 1 <= NSTG, "prologue fills distinct stages");
+    if (sk_elect_one())
+        for (int i = 0; i <= PF && i < NB; ++i) issue(i, i);   // tiles 0 .. PF (tile j + PF + 1 follows block j)
+    int st_issue = (PF + 1) % NSTG;                            // stage of the next tile to fetch
+    int st_wait = 0;                                           // stage and phase parity of the current block's tile
+    uint32_t par_wait = 0;
 
     // loop-carried state
     float dp = NEG;
@@ -324,6 +341,14 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     // rows of lanes 31 and 30 are read back (the other lanes write to a scratch area, one column each)
     const uint32_t pub_sa = sm0 + SM::PUB +
                             ((has_right && lane == 31) ? 0u : (has_right && lane == 30) ? 64u : 128u + 4u * (uint32_t)lane);
+    // running pointers of the per-block stores: this lane's backpointer word of row j - q_rows, and the
+    // exchange word it publishes (lanes 0-15: adv31 of frame 16 j + lane - 31 D, lanes 16-31: adv30 of frame
+    // 16 j + lane - 16 - 30 D)
+    uint32_t *bp_ptr = g_bp + (int64_t)(-q_rows) * Sp + s;
+    int bp_row = -q_rows;
+    int pub_t = (lane & 15) - (31 - (lane >> 4)) * D;
+    unsigned long long *pub_ptr = reinterpret_cast<unsigned long long *>(my_x + pub_t) + (lane >> 4);
+    const uint32_t pubrd_sa = sm0 + SM::PUB + 4u * (uint32_t)(16 * (lane >> 4) + (lane & 15));
     float *g_dp = (KEEP && m.dp_off >= 0) ? ws.dp_store + m.dp_off + (int64_t)w * NB * 512 : nullptr;
 
     // exchange slots of the NEXT block, fetched one block early (the left strip is normally that far ahead)
@@ -332,9 +357,11 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     if (slot_needed(0)) xv_next = sk_ld_slot(left_x + lane);
 
     for (int j = 0; j < NB; ++j) {
-        __syncwarp();                                          // every lane is done with the stage refilled below
-        if (lane == 0 && j + PF < NB) issue(j + PF);
-        sk_mbar_wait(sm0 + SM::FULL + 8u * (uint32_t)(j % NSTG), (uint32_t)((j / NSTG) & 1));
+        sk_mbar_wait(sm0 + SM::FULL + 8u * (uint32_t)st_wait, par_wait);
+        if (++st_wait == NSTG) {
+            st_wait = 0;
+            par_wait ^= 1u;
+        }
 
         if (has_left) {
             // the left strip's advance scores for frames 16 j .. 16 j + 15 (ghost lane 0 is at frame n,
@@ -362,6 +389,7 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         const uint32_t e_sa = ghost ? feed_sa + (uint32_t)(j & 1) * (16u * SK_ROW_B) : tile_sa + (uint32_t)u_row * SK_ROW_B;
         const uint32_t d_sa = edge_sa + (uint32_t)u_row * 8u;
         const uint32_t k_sa = dpst_sa + (uint32_t)(j & 1) * 2048u;
+        const uint32_t p_sa = pub_sa + (uint32_t)(j & 1) * 320u;
         // all 32 lanes inside frames 1 .. T-1 for all 16 iterations?
         const bool steady = (16 * j - 31 * D >= 1) && (16 * j + 15 <= T - 1);
         uint32_t acc = 0;                                      // this block's backpointer bits, by frame residue
@@ -387,7 +415,7 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
 #pragma unroll
                 for (int i = 0; i + 1 < 2 * D; ++i) q2[i] = q2[i + 1];
                 q2[2 * D - 1] = n2;
-                sk_sts_f32(pub_sa + 4u * k, advx);
+                sk_sts_f32(p_sa + 4u * k, advx);
                 const float mm = fmaxf(stay, up1);
                 const bool b1 = up1 > stay, b2 = up2 > mm;
                 const double pe = __dmul_rn((double)e, ratio);
@@ -437,7 +465,7 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                     const float advx = ghost ? e : adv;
                     r1[k + D] = fminf(__shfl_up_sync(0xffffffffu, advx, 1), cap1);
                     r2[k + 2 * D] = fminf(__shfl_up_sync(0xffffffffu, advx, 2), jcap);
-                    sk_sts_f32(pub_sa + 4u * k, advx);
+                    sk_sts_f32(p_sa + 4u * k, advx);
                     const double pe = __dmul_rn((double)e, ratio);
                     sk_select(r1[k], stay, r2[k], pe, sp_hi, mr, dp, P, acc);
                     mr = __funnelshift_l(mr, mr, 1);
@@ -459,7 +487,7 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                     const float advx = ghost ? e : adv;
                     r1[k + D] = fminf(__shfl_up_sync(0xffffffffu, advx, 1), cap1);
                     r2[k + 2 * D] = fminf(__shfl_up_sync(0xffffffffu, advx, 2), jcap);
-                    sk_sts_f32(pub_sa + 4u * k, advx);
+                    sk_sts_f32(p_sa + 4u * k, advx);
                     const double pe = __dmul_rn((double)e, ratio);
                     sk_select_guarded(r1[k], stay, r2[k], pe, sp_hi, mr, live, dp, P, acc);
                     mr = __funnelshift_l(mr, mr, 1);
@@ -478,33 +506,32 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         // Backpointer words.  A lane's 16 frames of a block straddle two 16-frame rows: `bits` holds the
         // first part of row j - q_rows (from the previous block), its last part is acc[hi_mask]; the rest
         // of acc opens the next row.
-        {
-            const int row = j - q_rows;
-            if (real && row >= 0 && row < n_rows) g_bp[(int64_t)row * Sp + s] = bits | (acc & hi_mask);
-            bits = acc & ~hi_mask;
-        }
+        if (real && bp_row >= 0 && bp_row < n_rows) *bp_ptr = bits | (acc & hi_mask);
+        bits = acc & ~hi_mask;
+        bp_ptr += Sp;
+        ++bp_row;
+        if (KEEP) hfa_fence_async_smem();                      // this block's dp rows -> visible to the bulk store
+        __syncwarp();                                          // every lane is done with this block's stage reads,
+                                                               // staging writes and the stage refilled below
         if (has_right) {
-            // the 16 advance scores lane 31 (frames 16 j - 31 D ..) and lane 30 (frames 16 j - 30 D ..) have
-            // parked: lanes 0-15 / 16-31 publish them, one tagged 64-bit word each (frames 1 .. T-1 only)
-            __syncwarp();
-            const int half = lane >> 4, i = lane & 15;
-            const int t = 16 * j + i - (31 - half) * D;
-            if (t >= 1 && t < T)
-                sk_st_word(reinterpret_cast<unsigned long long *>(my_x + t) + half,
-                           sk_pack(sk_lds_f32(sm0 + SM::PUB + 4u * (uint32_t)(16 * half + i)), (uint32_t)t + 1u));
-            __syncwarp();
+            // the 16 advance scores lanes 31 and 30 have parked: lanes 0-15 / 16-31 publish them, one tagged
+            // 64-bit word each (frames 1 .. T-1 only; the staging is double-buffered)
+            if (pub_t >= 1 && pub_t < T)
+                sk_st_word(pub_ptr, sk_pack(sk_lds_f32(pubrd_sa + (uint32_t)(j & 1) * 320u), (uint32_t)pub_t + 1u));
+            pub_t += 16;
+            pub_ptr += 32;                                     // 16 slots of two words
         }
-        if (KEEP && g_dp != nullptr) {
-            // this block's 16 rows of dp leave as one bulk store; the staging tile written two blocks
-            // ago must have been read out before the next block overwrites it
-            hfa_fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
+        if (sk_elect_one()) {
+            if (KEEP && g_dp != nullptr) {
+                // the block's 16 rows of dp leave as one bulk store; the staging tile written two blocks
+                // ago must have been read out before the next block overwrites it
                 sk_bulk_store(g_dp + (int64_t)j * 512, sm0 + SM::DPST + (uint32_t)(j & 1) * 2048u, 2048u);
                 hfa_bulk_commit();
                 sk_bulk_wait_read_1();
             }
+            if (j + PF + 1 < NB) issue(j + PF + 1, st_issue);  // into the stage last read during this block
         }
+        if (++st_issue == NSTG) st_issue = 0;
         u_row += 16;
         if (u_row >= R) u_row -= R;
     }
@@ -515,7 +542,7 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
         if (s == S - 1) ws.dp_last[2 * u] = dp;
         if (s == S - 2) ws.dp_last[2 * u + 1] = dp;
     }
-    if (KEEP && lane == 0) hfa_bulk_wait_all();
+    if (KEEP && sk_elect_one()) hfa_bulk_wait_all();
 }
 
 template <int D, int NSTG, bool KEEP, bool DUMP>
