@@ -16,7 +16,7 @@ HFA_OK = 0
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 UTT_OK, UTT_EMPTY, UTT_BAD_ID, UTT_NO_STATES, UTT_INFEASIBLE, UTT_TOO_MANY_STATES = range(6)
 MAX_STATES = 8192
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HfaError(RuntimeError):
@@ -48,6 +48,8 @@ SYMBOLS = {
     "hfa_plan_routing": (C.c_int, [_vp, C.POINTER(_i32 * 8)]),
     "hfa_plan_upload": (C.c_int, [_vp, _vp, _vp]),
     "hfa_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hfa_set_inputs_device": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "hfa_release_thread_resources": (None, []),
     "hfa_emission": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hfa_pack_emissions": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hfa_viterbi_forward": (C.c_int, [_vp, _vp, _vp, _vp]),

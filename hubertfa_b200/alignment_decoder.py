@@ -174,9 +174,9 @@ class AlignmentDecoder:
         S = np.array([len(i) for i in ids_list], dtype=np.int32)
         ids = np.concatenate(ids_list).astype(np.int32) if len(ids_list) else np.zeros(0, np.int32)
         plan = ops.AlignPlan(T, S, ids, self.vocab["vocab_size"], self.frame_length)
-        # One device context and the C ABI called directly (the torch custom ops wrap the same entry
-        # points; their dispatcher costs ~50 us per call, which matters for the one-utterance-per-call
-        # pattern of predict_step).  Pinned result buffers are kept across calls (grow-only).
+        # Collation tables go through the plan's ctypes methods; the compute is ONE dispatch of the
+        # hfa::align_batch custom op (emission -> DP -> backtrace on the current stream).  Pinned result
+        # buffers are kept across calls (grow-only).
         lib = _lib.load()
         n = len(frames)
         tabs = [np.fromiter((f.data_ptr() for f in frames), dtype=np.int64, count=n),
@@ -193,8 +193,7 @@ class AlignmentDecoder:
             sp, h, wp = int(stream.cuda_stream), plan.handle, ws.data_ptr()
             _lib.check(lib.hfa_plan_upload(h, wp, sp), "hfa_plan_upload")
             _lib.check(lib.hfa_set_inputs(h, wp, *[a.ctypes.data for a in tabs], sp), "hfa_set_inputs")
-            _lib.check(lib.hfa_align_batch(h, wp, ops.TORCH_TO_DTYPE[dtype], res.data_ptr(),
-                                           fc.data_ptr() if fc is not None else None, sp), "hfa_align_batch")
+            ops.align_batch(ws, h, ops.TORCH_TO_DTYPE[dtype], res, fc)
             host = self._pinned("res", plan.result_bytes, torch.uint8)
             host.copy_(res, non_blocking=True)
             fc_host = None

@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <numeric>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda.h>      // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
@@ -91,9 +93,14 @@ struct HfaSideStreams {
     cudaStream_t stream[HFA_NUM_CLASSES] = {};
     cudaEvent_t fork = nullptr, join[HFA_NUM_CLASSES] = {};
 };
-HfaSideStreams *side_streams()
+std::vector<HfaSideStreams *> &side_pool()
 {
     thread_local std::vector<HfaSideStreams *> pool;
+    return pool;
+}
+HfaSideStreams *side_streams()
+{
+    std::vector<HfaSideStreams *> &pool = side_pool();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     for (HfaSideStreams *s : pool)
@@ -107,8 +114,22 @@ HfaSideStreams *side_streams()
              cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) { delete s; return nullptr; }
-    pool.push_back(s);
+    try {
+        pool.push_back(s);
+    } catch (const std::bad_alloc &) {
+        delete s;
+        return nullptr;
+    }
     return s;
+}
+
+int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+        return 148;                                            // B200
+    return n;
 }
 
 }  // namespace
@@ -151,10 +172,24 @@ struct hfa_plan {
             o_last = 0, o_dpst = 0, o_jump = 0, o_moves = 0, o_rowent = 0, o_band_items = 0, o_jblk_utt = 0, o_jblk_first = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, o_tmaps = 0, ws_bytes = 0;
     int32_t n_tmaps = 0;                       // banded utterances (one emission tensor map each)
     std::vector<unsigned char> head;           // host image of the head (without inputs)
-    // set by hfa_set_inputs: > 0 when every utterance's logits have unit column stride, element-
-    // aligned base pointers and positive row strides of at most this many elements (TMA path)
-    mutable int64_t max_row_stride = 0;
     HfaResultLayout res{};
+    // What hfa_set_inputs / hfa_set_inputs_device last stored in each workspace this plan was used with
+    // (one plan may serve several workspaces, from several host threads): > 0 when every utterance's
+    // logits have unit column stride, element-aligned base pointers and positive row strides of at most
+    // this many elements -- then the logits rows can travel by TMA.  A per-workspace record, not plan state.
+    mutable std::mutex layout_mu;
+    mutable std::unordered_map<const void *, int64_t> layout_of;
+    int64_t row_stride_of(const void *workspace) const
+    {
+        std::lock_guard<std::mutex> g(layout_mu);
+        auto it = layout_of.find(workspace);
+        return it == layout_of.end() ? 0 : it->second;
+    }
+    void set_row_stride(const void *workspace, int64_t v) const
+    {
+        std::lock_guard<std::mutex> g(layout_mu);
+        layout_of[workspace] = v;
+    }
 };
 
 namespace {
@@ -602,7 +637,7 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
     cudaError_t e = cudaMemcpyAsync(workspace, p->head.data(), (size_t)p->head_bytes,
                                     cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload");
-    if (p->n_tmaps > 0 && tensor_map_encoder() != nullptr) {
+    if (p->n_tmaps > 0 && tensor_map_encoder() != nullptr) try {
         // TMA tensor maps over emis[t][s] of the banded utterances (they hold the workspace address, so
         // they are built here): rank 2, f32, dims {Sp, T}, row pitch Sp * 4 B, box {32 K, 16}
         std::vector<CUtensorMap> maps((size_t)p->n_tmaps);
@@ -622,6 +657,8 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
         e = cudaMemcpyAsync(static_cast<unsigned char *>(workspace) + p->o_tmaps, maps.data(), maps.size() * 128,
                             cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload: tensor maps");
+    } catch (const std::bad_alloc &) {
+        return fail(HFA_ERR_NOMEM, "hfa_plan_upload: out of host memory");
     }
     if (p->band_bytes > 0) {       // band tickets + exchange slots start (and are left) all-zero
         e = cudaMemsetAsync(static_cast<unsigned char *>(workspace) + p->o_band_ticket, 0,
@@ -639,31 +676,70 @@ int hfa_set_inputs(const hfa_plan *p, void *workspace, const void *const *frame_
     if (p->n_utt == 0) return HFA_OK;
     if (!frame_ptrs || !frame_stride_t || !frame_stride_v || !edge_ptrs || !edge_stride)
         return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL input table");
-    std::vector<HfaInput> in((size_t)p->n_utt);
-    int64_t row_stride = 0;
-    bool contiguous = true;
-    for (int32_t b = 0; b < p->n_utt; ++b) {
-        if (p->utt[b].status == 0 && (!frame_ptrs[b] || !edge_ptrs[b]))
-            return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL logits pointer for utterance %d", b);
-        if (p->utt[b].status == 0) {
-            if (frame_stride_v[b] != 1 || frame_stride_t[b] < p->vocab ||
-                (reinterpret_cast<uintptr_t>(frame_ptrs[b]) & 3u))
-                contiguous = false;
-            row_stride = std::max(row_stride, frame_stride_t[b]);
+    try {
+        std::vector<HfaInput> in((size_t)p->n_utt);
+        int64_t row_stride = 0;
+        bool contiguous = true;
+        for (int32_t b = 0; b < p->n_utt; ++b) {
+            if (p->utt[b].status == 0 && (!frame_ptrs[b] || !edge_ptrs[b]))
+                return fail(HFA_ERR_ARG, "hfa_set_inputs: NULL logits pointer for utterance %d", b);
+            if (p->utt[b].status == 0) {
+                if (frame_stride_v[b] != 1 || frame_stride_t[b] < p->vocab ||
+                    (reinterpret_cast<uintptr_t>(frame_ptrs[b]) & 3u))
+                    contiguous = false;
+                row_stride = std::max(row_stride, frame_stride_t[b]);
+            }
+            in[b].frame = frame_ptrs[b];
+            in[b].edge = edge_ptrs[b];
+            in[b].frame_st = frame_stride_t[b];
+            in[b].frame_sv = frame_stride_v[b];
+            in[b].edge_st = edge_stride[b];
         }
-        in[b].frame = frame_ptrs[b];
-        in[b].edge = edge_ptrs[b];
-        in[b].frame_st = frame_stride_t[b];
-        in[b].frame_sv = frame_stride_v[b];
-        in[b].edge_st = edge_stride[b];
+        HfaLaunchCtx c = make_ctx(p, workspace, stream);
+        // pageable source: the runtime stages the table before returning, `in` may go out of scope
+        cudaError_t e = cudaMemcpyAsync(c.ws.inputs, in.data(), in.size() * sizeof(HfaInput),
+                                        cudaMemcpyHostToDevice, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_set_inputs: input table upload");
+        p->set_row_stride(workspace, contiguous ? row_stride : 0);
+    } catch (const std::bad_alloc &) {
+        return fail(HFA_ERR_NOMEM, "hfa_set_inputs: out of host memory");
     }
-    HfaLaunchCtx c = make_ctx(p, workspace, stream);
-    // pageable source: the runtime stages the table before returning, `in` may go out of scope
-    cudaError_t e = cudaMemcpyAsync(c.ws.inputs, in.data(), in.size() * sizeof(HfaInput),
-                                    cudaMemcpyHostToDevice, c.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "hfa_set_inputs: input table upload");
-    p->max_row_stride = contiguous ? row_stride : 0;
     return HFA_OK;
+}
+
+static_assert(sizeof(HfaInputDesc) == sizeof(HfaInput), "the public descriptor is the kernels' own");
+
+int hfa_set_inputs_device(const hfa_plan *p, void *workspace, const HfaInputDesc *table, int64_t max_row_stride,
+                          void *stream)
+{
+    if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_set_inputs_device: NULL plan/workspace");
+    if (p->n_utt == 0) return HFA_OK;
+    if (!table) return fail(HFA_ERR_ARG, "hfa_set_inputs_device: NULL table");
+    if (max_row_stride < 0) return fail(HFA_ERR_ARG, "hfa_set_inputs_device: negative row stride");
+    HfaLaunchCtx c = make_ctx(p, workspace, stream);
+    // device -> device: a plain copy node, so the whole step can be captured into a CUDA graph
+    cudaError_t e = cudaMemcpyAsync(c.ws.inputs, table, (size_t)p->n_utt * sizeof(HfaInput),
+                                    cudaMemcpyDeviceToDevice, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_set_inputs_device: table copy");
+    try {
+        p->set_row_stride(workspace, max_row_stride);
+    } catch (const std::bad_alloc &) {
+        return fail(HFA_ERR_NOMEM, "hfa_set_inputs_device: out of host memory");
+    }
+    return HFA_OK;
+}
+
+void hfa_release_thread_resources(void)
+{
+    for (HfaSideStreams *s : side_pool()) {
+        for (int i = 0; i < HFA_NUM_CLASSES; ++i) {
+            if (s->stream[i]) cudaStreamDestroy(s->stream[i]);
+            if (s->join[i]) cudaEventDestroy(s->join[i]);
+        }
+        if (s->fork) cudaEventDestroy(s->fork);
+        delete s;
+    }
+    side_pool().clear();
 }
 
 int hfa_emission(const hfa_plan *p, void *workspace, int32_t dtype, void *stream)
@@ -673,7 +749,7 @@ int hfa_emission(const hfa_plan *p, void *workspace, int32_t dtype, void *stream
     if (dtype < 0 || dtype > 2) return fail(HFA_ERR_ARG, "hfa_emission: bad dtype %d", dtype);
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
     static const bool no_tma = [] { const char *v = std::getenv("HFA_EMISSION_NO_TMA"); return v && v[0] == '1'; }();
-    const int64_t row_stride = no_tma ? 0 : p->max_row_stride;
+    const int64_t row_stride = no_tma ? 0 : p->row_stride_of(workspace);
     // The persistent (TMA) emission kernel leaves the edge stream to its own small kernel, forked
     // onto a side stream so that the two overlap and joined before anything downstream.  The fork
     // point has to be recorded BEFORE the emission launch is queued.
@@ -832,26 +908,27 @@ int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame
     return HFA_OK;
 }
 
-static bool fused_ok(const hfa_plan *p, int32_t dtype)
+static bool fused_ok(const hfa_plan *p, const void *workspace, int32_t dtype)
 {
+    const int64_t max_row_stride = p->row_stride_of(workspace);
     const bool all_banded = p->warp_all_count == 0 && p->lat_count == 0 &&
                             p->class_count[HFA_NUM_CLASSES] == 0 && !p->band_items.empty();
     const bool skewed = p->band_skew[0] > 0 || p->band_skew[1] > 0;   // no producer warp there to fuse into
-    return all_banded && !skewed && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && p->max_row_stride > 0 &&
-           p->vocab <= 256 && p->max_row_stride * 4 * HFA_TILE_T <= 48 * 1024;
+    return all_banded && !skewed && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && max_row_stride > 0 &&
+           p->vocab <= 256 && max_row_stride * 4 * HFA_TILE_T <= 48 * 1024;
 }
 
 int hfa_forward_fused(const hfa_plan *p, void *workspace, int32_t dtype, void *stream)
 {
     if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_forward_fused: NULL plan/workspace");
-    if (!fused_ok(p, dtype))
+    if (!fused_ok(p, workspace, dtype))
         return fail(HFA_ERR_UNSUPPORTED, "hfa_forward_fused: needs an all-banded plan that keeps dp, f32 logits "
                                          "with contiguous rows (set by hfa_set_inputs) and V <= 256");
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
     cudaError_t e = hfa_launch_edge(c, p->row_blocks[p->n_utt], dtype);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_forward_fused: edge kernel");
     g_launches += 1;
-    return viterbi_forward_impl(p, workspace, nullptr, stream, p->max_row_stride);
+    return viterbi_forward_impl(p, workspace, nullptr, stream, p->row_stride_of(workspace));
 }
 
 int64_t hfa_plan_algorithmic_bytes_fused(const hfa_plan *p, int32_t dtype)
@@ -882,7 +959,7 @@ int hfa_align_batch(const hfa_plan *p, void *workspace, int32_t dtype, void *res
     for (const HfaUtt &m : p->utt) n_valid += (m.status == 0);
     const bool unsplit = (int64_t)p->band_items.size() == n_valid;
     int rc;
-    if ((fused_mode == 1 || (fused_mode == -1 && unsplit)) && fused_ok(p, dtype)) {
+    if ((fused_mode == 1 || (fused_mode == -1 && unsplit)) && fused_ok(p, workspace, dtype)) {
         rc = hfa_forward_fused(p, workspace, dtype, stream);
     } else {
         rc = hfa_emission(p, workspace, dtype, stream);

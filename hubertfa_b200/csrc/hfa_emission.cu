@@ -545,7 +545,9 @@ static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_
                                                           HFA_EMIS_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
         per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-        const int grid = blocks < 148 * per_sm ? blocks : 148 * per_sm;
+        int dev = 0, n_sm = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = blocks < n_sm * per_sm ? blocks : n_sm * per_sm;
         *n_launched = 2;     // tells the caller to launch hfa_launch_edge as well (on a forked stream)
         hfa_emission_stream_kernel<TIn><<<grid, HFA_EMIS_WARPS * 32, smem, c.stream>>>(
             c.ws, blocks, V, max_sp, (int)stage);

@@ -105,6 +105,31 @@ class AlignPlan:
             check(self._lib.hfa_set_inputs(self._h, workspace.data_ptr(), *[a.ctypes.data for a in tabs],
                                            _stream_ptr()), "hfa_set_inputs")
 
+    INPUT_DESC = np.dtype([("frame", np.int64), ("edge", np.int64), ("frame_stride_t", np.int64),
+                           ("frame_stride_v", np.int64), ("edge_stride", np.int64)])    # = HfaInputDesc
+
+    def input_table(self, frame_ptrs, frame_st, frame_sv, edge_ptrs, edge_st) -> np.ndarray:
+        """Host image of the per-utterance input table (HfaInputDesc[n_utt]) plus the row-stride promise
+        ``set_inputs_device`` needs: returns (table as uint8 array, max_row_stride)."""
+        tab = np.zeros(self.n_utt, dtype=self.INPUT_DESC)
+        for name, a in zip(self.INPUT_DESC.names, (frame_ptrs, edge_ptrs, frame_st, frame_sv, edge_st)):
+            tab[name] = np.asarray(a, dtype=np.int64)
+        ok = self.T > 0
+        tma = bool(np.all(tab["frame_stride_v"][ok] == 1) and np.all(tab["frame_stride_t"][ok] >= self.vocab_size)
+                   and np.all(tab["frame"][ok] % 4 == 0))
+        stride = int(tab["frame_stride_t"][ok].max()) if ok.any() else 0
+        return tab.view(np.uint8), (stride if tma else 0)
+
+    def set_inputs_device(self, workspace: torch.Tensor, table: torch.Tensor, max_row_stride: int) -> None:
+        """The input table already on the device (uint8 tensor holding HfaInputDesc[n_utt]): a device-to-
+        device copy, capturable into a CUDA graph (hfa_set_inputs_device)."""
+        _require_cuda(table, "input table")
+        if table.numel() * table.element_size() < self.n_utt * self.INPUT_DESC.itemsize:
+            raise HfaError("input table too small for this plan")
+        with torch.cuda.device(workspace.device):
+            check(self._lib.hfa_set_inputs_device(self._h, workspace.data_ptr(), table.data_ptr(),
+                                                  int(max_row_stride), _stream_ptr()), "hfa_set_inputs_device")
+
     def views(self, blob: np.ndarray) -> dict:
         """Typed numpy views into a host copy of the result blob."""
         L, n, ns = self.layout, self.n_utt, self.total_states
@@ -198,6 +223,47 @@ def forward_fused(workspace: torch.Tensor, plan: int, dtype: int) -> None:
     raises HfaError when the plan / inputs do not qualify)."""
     with torch.cuda.device(workspace.device):
         check(_lib.load().hfa_forward_fused(plan, workspace.data_ptr(), dtype, _stream_ptr()), "hfa_forward_fused")
+
+
+class GraphedStep:
+    """One whole step -- (optionally) the device-side input table copy, hfa_align_batch, the download of
+    the result blob into pinned host memory -- captured ONCE into a CUDA graph and replayed with a single
+    launch.  For fixed-shape batches that are aligned over and over (a serving loop over length buckets, the
+    benchmark): the five kernel launches, the stream forks and their event records stop costing host time.
+
+    plan / workspace must be uploaded (``plan.upload``) and, unless ``table`` is given, have their inputs
+    set before the capture.  ``table``: device uint8 tensor with HfaInputDesc[n_utt]; it is re-read at every
+    replay, so the caller may point the step at new logits by rewriting it (same shapes)."""
+
+    def __init__(self, plan: AlignPlan, workspace: torch.Tensor, result: torch.Tensor, host_result: torch.Tensor,
+                 dtype: int, frame_conf: Optional[torch.Tensor] = None, table: Optional[torch.Tensor] = None,
+                 max_row_stride: int = 0, warmup: int = 2):
+        if not host_result.is_pinned():
+            raise HfaError("host_result must be pinned memory")
+        self.plan, self.host_result = plan, host_result
+        dev = workspace.device
+
+        def body():
+            if table is not None:
+                plan.set_inputs_device(workspace, table, max_row_stride)
+            align_batch(workspace, plan.handle, dtype, result, frame_conf)
+            host_result.copy_(result, non_blocking=True)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                  # warm-up outside the capture (lazy module loads)
+                for _ in range(max(warmup, 1)):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                body()
+
+    def replay(self) -> None:
+        """Enqueues the step on the current stream (results are in ``host_result`` once it has drained)."""
+        self.graph.replay()
 
 
 def unpack_backptr(plan: AlignPlan, workspace: torch.Tensor, utt: int) -> torch.Tensor:

@@ -38,16 +38,30 @@ def longest_first_order(T) -> np.ndarray:
 
 
 class BufferPool:
-    """Reusable device / pinned-host byte buffers, handed out in call order and rewound by
-    ``reset()`` -- lets successive batches reuse their staging memory (pinned allocation is slow)."""
+    """Reusable device / pinned-host byte buffers -- lets successive batches reuse their staging memory
+    (pinned allocation is slow).  Device buffers are scratch: handed out in call order and rewound by
+    ``reset()``.  Pinned buffers carry RESULTS: ``take_pinned`` checks one out and it stays out until the
+    ``PipelineResult`` that owns it gives it back (``give_pinned``), so a result a caller still holds is
+    never overwritten by a later batch."""
 
     def __init__(self, device):
         self.device = device
         self._dev, self._pin = [], []
         self._di = self._pi = 0
+        self._pin_free = []
 
     def reset(self):
         self._di = self._pi = 0
+
+    def take_pinned(self, nbytes):
+        """A pinned buffer of at least nbytes that no live result owns (first fit, else a new one)."""
+        for i, buf in enumerate(self._pin_free):
+            if buf.numel() >= nbytes:
+                return self._pin_free.pop(i)
+        return torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, pin_memory=True)
+
+    def give_pinned(self, buf):
+        self._pin_free.append(buf)
 
     @staticmethod
     def _take(store, i, nbytes, make):
@@ -85,9 +99,9 @@ class PipelineResult(dict):
     result blobs on first access -- the blobs are on the host when ``run`` returns, the Python-side
     slicing is not part of the critical path of a pipeline that only needs some of them."""
 
-    def __init__(self, n_utt, live, lib):
+    def __init__(self, n_utt, live, lib, pool=None):
         super().__init__()
-        self._n, self._live, self._lib = n_utt, live, lib
+        self._n, self._live, self._lib, self._pool = n_utt, live, lib, pool
         self.d2h_bytes = sum(int(item[2].total_bytes) for item in live)
 
     def _materialise(self):
@@ -97,7 +111,8 @@ class PipelineResult(dict):
         out = dict(status=np.empty(n, np.int32), n_seg=np.empty(n, np.int32), total_conf=np.empty(n, np.float32),
                    final_score=np.empty(n, np.float32), chunks=[])
         for c, h, lay, host_res, _, _ in self._live:
-            blob = host_res.numpy()
+            # a private copy: the pinned buffer goes back to the pool below and later batches reuse it
+            blob = host_res.numpy()[:int(lay.total_bytes)].copy()
             m, ns = c.b1 - c.b0, int(c.seg_off[-1])
 
             def v(off, dtype, count, blob=blob):
@@ -126,9 +141,12 @@ class PipelineResult(dict):
         return True
 
     def _release(self):
+        """Destroys the chunk plans and hands the pinned result buffers back to the pool."""
         if self._live is not None:
             for item in self._live:
                 self._lib.hfa_plan_destroy(item[1])
+                if self._pool is not None:
+                    self._pool.give_pinned(item[3])
             self._live = None
 
     def __getitem__(self, key):
@@ -267,7 +285,7 @@ class HostBatchAligner:
                 lib.hfa_plan_result_layout(h, C.byref(lay))
                 ws = pool.device_bytes(max(int(lib.hfa_plan_workspace_bytes(h)), 256))
                 res = pool.device_bytes(int(lay.total_bytes))
-                host_res = pool.pinned_bytes(int(lay.total_bytes))
+                host_res = pool.take_pinned(int(lay.total_bytes))     # owned by the result until it lets go
                 st = c.stream
                 st.wait_stream(cur)
                 sp = int(st.cuda_stream)
@@ -279,7 +297,7 @@ class HostBatchAligner:
                 st.wait_event(landed[c.piece])
                 _lib.check(lib.hfa_align_batch(h, wp, self.dt, res.data_ptr(), None, sp), "hfa_align_batch")
                 with torch.cuda.stream(st):
-                    host_res.copy_(res, non_blocking=True)
+                    host_res[:int(lay.total_bytes)].copy_(res, non_blocking=True)
                     if profile:
                         done = torch.cuda.Event(enable_timing=True)
                         done.record(st)
@@ -287,7 +305,7 @@ class HostBatchAligner:
                 live.append((c, h, lay, host_res, ws, res))
             for item in live:
                 item[0].stream.synchronize()
-        out = PipelineResult(self.n_utt, live, lib)
+        out = PipelineResult(self.n_utt, live, lib, pool)
         self.d2h_bytes = out.d2h_bytes
         if profile:
             dict.__setitem__(out, "profile", [dict(landed_ms=ev0.elapsed_time(l), done_ms=ev0.elapsed_time(d),

@@ -9,7 +9,11 @@
  * Conventions
  *   - plain C types only; every pointer marked [dev] is device memory owned by the caller, [host]
  *     is host memory owned by the caller.  The library never allocates device memory and never
- *     synchronises the stream; kernels are enqueued on the cudaStream_t passed as void*.
+ *     synchronises the stream; kernels are enqueued on the cudaStream_t passed as void*.  The one
+ *     resource it creates itself: a few non-blocking side streams and timing-free events per host
+ *     thread and device, made on first use (independent kernels of one call are forked onto them and
+ *     joined back into the caller's stream before the call returns; capturable into a CUDA graph) and
+ *     destroyed by hfa_release_thread_resources().
  *   - every function returns HFA_OK (0) or a negative HFA_ERR_* code and never throws;
  *     hfa_last_error() returns a thread-local message for the last failure.
  *   - a batch is ragged: utterance b has T[b] frames and S[b] phoneme states.  Per-frame arrays
@@ -26,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HFA_ABI_VERSION 1
+#define HFA_ABI_VERSION 2
 
 enum {
     HFA_OK = 0,
@@ -71,6 +75,9 @@ typedef struct HfaResultLayout {
 /* ---- library ------------------------------------------------------------------------------ */
 int hfa_abi_version(void);
 const char *hfa_last_error(void);
+/* destroys the side streams / events the calling host thread made (see the conventions above); no
+ * library call of this thread may be in flight.  They are re-created on the next use. */
+void hfa_release_thread_resources(void);
 
 /* ---- collation (host only; replaces the reference's one-utterance-per-call loop, infer.py:60) */
 /* T, S: [n_utt] host.  ph_ids: concatenated phoneme ids of all utterances, [sum S] host
@@ -115,10 +122,25 @@ int hfa_plan_upload(const hfa_plan *plan, void *workspace /*[dev]*/, void *strea
  * last (always true for views of a larger tensor and for allocator-aligned buffers).
  * The tables are [host] arrays of [dev] pointers; this call copies them into the workspace (a
  * pageable-memory H2D copy, so it is NOT capturable into a CUDA graph; every other compute entry
- * point only launches kernels and is). */
+ * point only launches kernels and is).  What is recorded is per (plan, workspace): one plan may be
+ * uploaded to several workspaces, each with its own inputs. */
 int hfa_set_inputs(const hfa_plan *plan, void *workspace, const void *const *frame_ptrs,
                    const int64_t *frame_stride_t, const int64_t *frame_stride_v,
                    const void *const *edge_ptrs, const int64_t *edge_stride, void *stream);
+
+/* The same table, already in device memory: [dev] HfaInputDesc[n_utt].  A device-to-device copy, so the
+ * whole step (this call, hfa_align_batch, the caller's D2H copy) can be captured into a CUDA graph and
+ * replayed while the caller rewrites the table between replays.  The library cannot look into the table:
+ * max_row_stride > 0 promises that every utterance has frame_stride_v == 1, a 4-byte aligned frame
+ * pointer and vocab_size <= frame_stride_t <= max_row_stride (the TMA-fed emission kernel is used then);
+ * pass 0 for anything else. */
+typedef struct HfaInputDesc {
+    const void *frame;        /* [dev] logits of the utterance, element (t, v) at frame[t*frame_stride_t + v*frame_stride_v] */
+    const void *edge;         /* [dev] edge logits, element t at edge[t*edge_stride]                                          */
+    int64_t frame_stride_t, frame_stride_v, edge_stride;   /* in elements */
+} HfaInputDesc;
+int hfa_set_inputs_device(const hfa_plan *plan, void *workspace, const HfaInputDesc *table /*[dev]*/,
+                          int64_t max_row_stride, void *stream);
 int hfa_emission(const hfa_plan *plan, void *workspace, int32_t dtype, void *stream);
 
 /* ---- stage 1': the reference's forward_pass inputs, given directly (parity tests) ----------- */

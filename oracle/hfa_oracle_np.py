@@ -5,7 +5,7 @@ oracle (the first is ``oracle/hfa_oracle.c``): every array carries an explicit d
 mixed f32/f64 rounding sequence of the reference is visible in the code.
 
 Reference: ``tools/alignment_decoder.py`` (cited as ``ad:<line>`` below).
-Parity status: PINNED -- ``tests/test_oracle_vs_reference.py`` compares this file with the
+Parity status: PINNED -- ``tests/test_oracle_golden.py`` compares this file with the
 unmodified reference wherever ``/root/reference`` exists, and ``tests/golden/*.npz`` holds
 reference outputs for the machines where it does not.
 

@@ -218,3 +218,97 @@ int main(void) {
                            str(src), "-o", str(exe), "-L", libdir, "-l:libhfa_align.so", f"-Wl,-rpath,{libdir}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+
+
+def test_corpus_plan_layout_mirrors_the_library():
+    """hubertfa_b200.corpus reserves and parses chunk result blobs from (n_utt, sum S) alone -- every rank
+    must derive the same offsets without talking to the others; it has to agree with hfa_plan_create."""
+    from hubertfa_b200 import ops, synth
+    from hubertfa_b200.corpus import CorpusPlan
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 3, 7, 64, 257):
+        T = rng.integers(1, 400, n).astype(np.int32)
+        S = rng.integers(1, 90, n).astype(np.int32)
+        ids = synth.make_ids_batch(T, S, 39, seed=n)
+        plan = ops.AlignPlan(T, S, np.concatenate(ids), 39, 0.02)
+        ns = int(S.sum())
+        assert plan.result_bytes <= CorpusPlan.result_bytes(n, ns)
+        a16 = lambda b: (b + 15) // 16 * 16
+        o, L = 0, plan.layout
+        for name, nb in (("status", 4 * n), ("n_seg", 4 * n), ("end_state", 4 * n), ("final_score", 4 * n),
+                         ("total_conf", 4 * n), ("ph_idx_seq", 4 * ns), ("ph_time_int", 4 * ns), ("intervals", 16 * ns)):
+            assert getattr(L, name) == o, name
+            o += a16(nb)
+    # sharding + chunking: every utterance in exactly one chunk of exactly one rank, blobs do not overlap
+    T, S = synth.sample_shapes(3000, seed=4)
+    cp = CorpusPlan(T, S, synth.make_ids_batch(T, S, 63, seed=4), 63, 0.02, 4, 20_000_000)
+    seen = np.concatenate([np.concatenate(c) for c in cp.chunks])
+    assert np.array_equal(np.sort(seen), np.arange(3000))
+    offs = [o for r in cp.blob_off for o in r] + [cp.total_result_bytes]
+    assert all(b > a for a, b in zip(offs[:-1], offs[1:]))
+    loads = [cp.cells_of_rank(r) for r in range(4)]
+    assert max(loads) <= 1.02 * min(loads)
+    for r in range(4):
+        for idx in cp.chunks[r]:
+            assert int((T[idx].astype(np.int64) * S[idx]).sum()) <= 20_000_000 or len(idx) == 1
+
+
+def _corpus_gather_worker(rank, world, port, name, q):
+    import torch.distributed as dist
+    from hubertfa_b200 import ops, synth
+    from hubertfa_b200.corpus import CorpusPlan, SharedHostBuffer, all_status_ok, read_results
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    T, S = synth.sample_shapes(200, seed=12, min_s=1, max_s=4, s_lo=3, s_hi=40)
+    ids = synth.make_ids_batch(T, S, 39, seed=12)
+    cp = CorpusPlan(T, S, ids, 39, 0.02, world, 200_000)
+    host = None
+    if rank == 0:
+        host = SharedHostBuffer(name, cp.total_result_bytes, create=True)
+    dist.barrier()
+    if rank != 0:
+        host = SharedHostBuffer(name, cp.total_result_bytes, create=False)
+    # every rank fabricates the result blobs of ITS chunks (what the D2H copies would deliver): utterance u gets
+    # n_seg = 1 + u % 3 segments with ph_idx = u + j, time = 10 u + j
+    for k, idx in enumerate(cp.chunks[rank]):
+        plan = ops.AlignPlan(T[idx], S[idx], np.concatenate([ids[i] for i in idx]), 39, 0.02)
+        blob = np.zeros(plan.result_bytes, np.uint8)
+        v = plan.views(blob)
+        for j, u in enumerate(idx):
+            n = min(1 + int(u) % 3, int(S[u]))
+            o = int(plan.seg_off[j])
+            v["n_seg"][j] = n
+            v["ph_idx_seq"][o:o + n] = int(u) + np.arange(n)
+            v["ph_time_int"][o:o + n] = 10 * int(u) + np.arange(n)
+            v["total_conf"][j] = float(u)
+        o = cp.blob_off[rank][k]
+        host.array[o:o + plan.result_bytes] = blob
+    dist.barrier()                                   # the "gather": rank 0 now simply reads
+    if rank == 0:
+        ok = all_status_ok(cp, host)
+        res = read_results(cp, host)
+        good = ok and len(res) == 200
+        for u in range(200):
+            n = min(1 + u % 3, int(S[u]))
+            good &= list(res[u]["ph_idx_seq"]) == [u + j for j in range(n)]
+            good &= list(res[u]["ph_time_int"]) == [10 * u + j for j in range(n)] and res[u]["total_conf"] == float(u)
+        q.put(bool(good))
+    dist.barrier()
+    host.close()
+    dist.destroy_process_group()
+
+
+def test_corpus_gather_through_shared_host_segment_world_size_2():
+    """The multi-GPU gather path without GPUs: two ranks write their chunks' result blobs into the shared
+    host segment at the offsets CorpusPlan derives, rank 0 reads everything back in corpus order."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    name = f"hfa_test_{os.getpid()}"
+    procs = [ctx.Process(target=_corpus_gather_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert q.get(timeout=5) is True
