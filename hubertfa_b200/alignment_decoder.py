@@ -153,6 +153,15 @@ class AlignmentDecoder:
             raise HfaError("no CUDA device: hubertfa_b200 has no CPU fallback")
         return torch.device("cuda", torch.cuda.current_device())
 
+    def _ids_of(self, ph_seq) -> np.ndarray:
+        """ad:35 (KeyError for an unknown phoneme) and the bounds numpy enforces at ad:38 / :239: ids are
+        used as indices into [V] arrays, so -V <= id < V, negative ones counting from the end."""
+        V = self.vocab["vocab_size"]
+        ids = np.array([self.vocab["vocab"][ph] for ph in ph_seq])
+        if ids.size and (ids.min() < -V or ids.max() >= V):
+            raise IndexError("phoneme id out of bounds for vocab_size")
+        return np.where(ids < 0, ids + V, ids)
+
     def _num_frames(self, wav_length, T: int) -> int:
         if wav_length is None:
             return T
@@ -226,15 +235,11 @@ class AlignmentDecoder:
                word_seq: list[str] = None,
                ph_idx_to_word_idx: list[int] = None
                ):
-        ph_seq_id = np.array([self.vocab["vocab"][ph] for ph in ph_seq])          # ad:35 (KeyError)
+        ph_seq_id = self._ids_of(ph_seq)                                           # ad:35 (KeyError), :38
         self.ph_seq_id = ph_seq_id
         if word_seq is None:                                                       # ad:41-43
             word_seq = ph_seq
             ph_idx_to_word_idx = np.arange(len(ph_seq))
-        if ph_seq_id.size and (ph_seq_id.min() < -self.vocab["vocab_size"]
-                               or ph_seq_id.max() >= self.vocab["vocab_size"]):
-            raise IndexError("phoneme id out of bounds for vocab_size")            # ad:38
-        ph_seq_id = np.where(ph_seq_id < 0, ph_seq_id + self.vocab["vocab_size"], ph_seq_id)
 
         if wav_length is not None:                                                 # ad:45-50
             num_frames = int(
@@ -266,25 +271,11 @@ class AlignmentDecoder:
         self.frame_confidence = fc.copy()
         self.final_score = np.float32(v["final_score"][0])
 
-        # ad:115-138 (host: string labels)
-        ph_seq_pred, ph_intervals_pred, word_seq_pred, word_intervals_pred = [], [], [], []
-        word_idx_last = -1
-        for i, ph_idx in enumerate(ph_idx_seq):
-            if ph_seq[ph_idx] == "SP":
-                continue
-            ph_seq_pred.append(ph_seq[ph_idx])
-            ph_intervals_pred.append(ph_intervals[i, :])
-            word_idx = ph_idx_to_word_idx[ph_idx]
-            if word_idx == word_idx_last:
-                word_intervals_pred[-1][1] = ph_intervals[i, 1]
-            else:
-                word_seq_pred.append(word_seq[word_idx])
-                word_intervals_pred.append([ph_intervals[i, 0], ph_intervals[i, 1]])
-                word_idx_last = word_idx
-        ph_seq_pred = np.array(ph_seq_pred)
-        ph_intervals_pred = np.array(ph_intervals_pred).clip(min=0, max=None)
-        word_seq_pred = np.array(word_seq_pred)
-        word_intervals_pred = np.array(word_intervals_pred).clip(min=0, max=None)
+        # ad:115-138: SP filter and word merge, the batch code path on a batch of one
+        is_sp = np.fromiter((p == "SP" for p in ph_seq), dtype=bool, count=len(ph_seq))
+        one = BatchAlignment(plan, v, [ph_seq], [word_seq], [ph_idx_to_word_idx], is_sp,
+                             np.asarray(ph_idx_to_word_idx, dtype=np.int64))
+        ph_seq_pred, ph_intervals_pred, word_seq_pred, word_intervals_pred, _ = one[0]
 
         self.ph_pred_seq = ph_seq_pred
         self.ph_intervals_pred = ph_intervals_pred
@@ -301,9 +292,7 @@ class AlignmentDecoder:
         with ``lengths`` giving T per utterance.  Host tensors are copied to the device first.
         """
         n = len(ph_seqs)
-        vocab = self.vocab["vocab"]
-        ids_list = [np.fromiter((vocab[p] for p in seq), dtype=np.int32, count=len(seq))
-                    for seq in ph_seqs]
+        ids_list = [self._ids_of(seq).astype(np.int32) for seq in ph_seqs]        # same checks as decode()
         if isinstance(ph_frame_logits, torch.Tensor):
             if lengths is None:
                 raise ValueError("packed logits need `lengths`")
@@ -317,6 +306,12 @@ class AlignmentDecoder:
             dev = self._device_for(ph_frame_logits[0])
             frames = [_as_2d(f).to(dev, non_blocking=True) for f in ph_frame_logits]
             edges = [_as_1d(e).to(dev, non_blocking=True) for e in ph_edge_logits]
+        # the reference applies .float() to both streams (ad:57,69): one element type per batch
+        dt0 = frames[0].dtype if n else torch.float32
+        if any(f.dtype != dt0 for f in frames) or dt0 not in ops.TORCH_TO_DTYPE:
+            dt0 = torch.float32
+        frames = [f if f.dtype == dt0 else f.to(dt0) for f in frames]
+        edges = [e if e.dtype == dt0 else e.to(dt0) for e in edges]
         if wav_lengths is not None:
             for b in range(n):
                 nf = self._num_frames(wav_lengths[b], frames[b].shape[0])

@@ -371,6 +371,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         int lat_mode = -1;
         if (const char *e = std::getenv("HFA_LATENCY_MODE")) lat_mode = e[0] - '0';
         std::vector<int32_t> lat, lat_band;
+        bool hybrid = false;             // lat_band holds only the costliest utterances of a big batch
         if (lat_mode == 1) {
             for (int c = 2; c < HFA_NUM_CLASSES; ++c) {
                 lat.insert(lat.end(), lists[c].begin(), lists[c].end());
@@ -394,6 +395,53 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                     p->class_count[c] = 0;
                 }
                 std::sort(lat_band.begin(), lat_band.end(), by_len);
+            } else if (skew_d > 0 && nb > 0) {
+                // Big batch, one warp per utterance -- except for its costliest utterances.  A single warp runs
+                // the recurrence of T frames x K states per lane at well under one instruction per cycle, so
+                // the few longest / widest utterances alone last about as long as the whole batch would on a
+                // perfectly filled machine, and the launch ends in a long, empty tail.  Those utterances are cut
+                // into strips of the skewed kernel instead (no redundant work, 2-5 warps each, no dp kept: they
+                // share the warp-per-utterance backtrace).  Cost unit: frames x states per lane; threshold =
+                // HFA_HYBRID x the per-scheduler share of the whole batch.
+                // MEASURED (B200, config 4): a loss -- DP stage 0.458 ms with no strips, 0.659 ms at 0.26 (2306
+                // strips), 0.917 ms at 0.15 (6758 strips): a strip spends ~1.5x the instructions per cell of the
+                // K-states-per-lane warp and holds 38 KB of shared memory.  Off by default; the knob stays.
+                double alpha = 0.0;
+                if (const char *e = std::getenv("HFA_HYBRID")) alpha = std::atof(e);
+                if (std::getenv("HFA_DP_MODE")) alpha = 0.0;       // per-class launch modes keep whole classes
+                auto ucost = [&](int32_t b) { return (int64_t)p->utt[b].T * ((p->utt[b].Sp + 31) / 32); };
+                int64_t sum_cost = 0;
+                for (int c = 0; c < HFA_NUM_CLASSES; ++c)
+                    for (int32_t b : lists[c]) sum_cost += ucost(b);
+                const double thresh = alpha * (double)sum_cost / (4.0 * sm_count());
+                // HFA_HYBRID_KIND=cta: the same utterances go to the multi-warp CTA kernel instead (2 states per
+                // lane, one barrier per frame)
+                const char *kind = std::getenv("HFA_HYBRID_KIND");
+                const bool to_cta = kind && kind[0] == 'c';
+                if (alpha > 0.0) {
+                    int64_t strips = 0;
+                    for (int c = (to_cta ? 2 : 1); c < HFA_NUM_CLASSES; ++c) {   // class 0 (S <= 32) is a single strip anyway
+                        std::vector<int32_t> keep;
+                        for (int32_t b : lists[c]) {
+                            if ((double)ucost(b) >= thresh && strips + n_bands(b, 1) <= 8 * band_max) {
+                                if (to_cta) {
+                                    lat.push_back(b);
+                                    p->lat_max_sp = std::max(p->lat_max_sp, p->utt[b].Sp);
+                                } else {
+                                    lat_band.push_back(b);
+                                }
+                                strips += n_bands(b, 1);
+                            } else {
+                                keep.push_back(b);
+                            }
+                        }
+                        lists[c].swap(keep);
+                        p->class_count[c] = (int32_t)lists[c].size();
+                    }
+                    std::sort(lat_band.begin(), lat_band.end(), by_len);
+                    std::sort(lat.begin(), lat.end(), by_len);
+                    hybrid = !lat_band.empty();
+                }
             }
         }
         std::vector<int32_t> big_band;
@@ -438,7 +486,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 // instead of re-running the serial chain along the path
                 p->utt[b].band_k = k;
                 p->utt[b].tmap = p->n_tmaps++;
-                if (keep_dp) {
+                if (keep_dp && !(hybrid && which == 0)) {
                     p->utt[b].dp_off = p->dp_store_elems;
                     // bands: one [T][32 k] block per band; strips: one 128-byte row per iteration
                     p->dp_store_elems += sd > 0 ? (int64_t)nb * hfa_skew_blocks(sd, p->utt[b].T) * 512

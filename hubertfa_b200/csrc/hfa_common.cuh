@@ -217,6 +217,21 @@ __device__ __forceinline__ float hfa_advance(float a, float curr, double ratio)
     return __double2float_rn(__dadd_rn((double)a, __dmul_rn((double)curr, ratio)));
 }
 
+// exp(x) for x <= 0 in the softmax normaliser (alignment_decoder.py:62-65).  Default: expf (1 ulp).
+// -DHFA_FAST_EXP: ex2.approx of x * log2(e), two instructions instead of eight, still inside the 4e-6 the
+// emission tests allow -- MEASURED on B200 config 4: no gain (emission stage 0.470 -> 0.481 ms: the kernel
+// waits on HBM, not on these instructions), so the exact one stays.
+__device__ __forceinline__ float hfa_exp_neg(float x)
+{
+#ifndef HFA_FAST_EXP
+    return expf(x);
+#else
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(x, 1.4426950408889634f)));
+    return y;
+#endif
+}
+
 template <typename T> __device__ __forceinline__ float hfa_to_float(T v);
 template <> __device__ __forceinline__ float hfa_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float hfa_to_float<__half>(__half v) { return __half2float(v); }

@@ -970,13 +970,13 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
 #pragma unroll
                         for (int j = 0; j < 16; ++j)     // entries past the end are -inf: exp = +0, sum unchanged
-                            sum = __fadd_rn(sum, expf(__fsub_rn(xv[j], mx)));
+                            sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(xv[j], mx)));
                     } else {
                         for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, row[kept_sm[k]]);
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
                         for (int k = part; k < n_kept; k += 4)
-                            sum = __fadd_rn(sum, expf(__fsub_rn(row[kept_sm[k]], mx)));
+                            sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(row[kept_sm[k]], mx)));
                     }
                     sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
                     sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));

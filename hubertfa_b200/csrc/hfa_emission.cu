@@ -158,7 +158,7 @@ hfa_emission_block_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         float sum = 0.0f;
-        for (int k = part; k < n_kept; k += 4) sum = __fadd_rn(sum, expf(__fsub_rn(row[kept_sm[k]], mx)));
+        for (int k = part; k < n_kept; k += 4) sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(row[kept_sm[k]], mx)));
         sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
         sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
         if (part == 0) stat_sm[tid >> 2] = make_float2(mx, logf(sum));
@@ -367,13 +367,13 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
 #pragma unroll
                 for (int j = 0; j < 16; ++j)         // entries past the end are -inf: exp = +0, sum unchanged
-                    sum = __fadd_rn(sum, expf(__fsub_rn(xv[j], mx)));
+                    sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(xv[j], mx)));
             } else {
                 for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, hfa_to_float<TIn>(row[kept_sm[k]]));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
                 for (int k = part; k < n_kept; k += 4)
-                    sum = __fadd_rn(sum, expf(__fsub_rn(hfa_to_float<TIn>(row[kept_sm[k]]), mx)));
+                    sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(hfa_to_float<TIn>(row[kept_sm[k]]), mx)));
             }
             sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
             sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
@@ -477,7 +477,7 @@ hfa_emission_wide_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
         }
         mr = warp_max(mr);
         float sum = 0.0f;
-        for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, expf(__fsub_rn(rowbuf[v], mr)));
+        for (int v = lane; v < V; v += 32) sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(rowbuf[v], mr)));
         const float l = logf(warp_sum(sum));
         __syncwarp();
         float *dst = g_out + (int64_t)t * Sp;

@@ -52,6 +52,7 @@ class BatchedPredictor:
         self.bucket_cells = float(bucket_cells)
         self.bucket_utts = int(bucket_utts)
         self.n_buckets = 0
+        self.error_log = []          # (wav_path, message) of utterances that could not be aligned
 
     def _flush(self, bucket, out):
         if not bucket:
@@ -61,7 +62,11 @@ class BatchedPredictor:
             [b[0][4] for b in bucket], [b[0][5] for b in bucket], wav_lengths=[b[0][1] for b in bucket])
         self.n_buckets += 1
         for j, (item, _, _) in enumerate(bucket):
-            ph_seq, ph_intervals, word_seq, word_intervals, confidence = res[j]
+            try:
+                ph_seq, ph_intervals, word_seq, word_intervals, confidence = res[j]
+            except Exception as e:                   # one bad utterance (empty after trimming, ...) must not
+                self.error_log.append((item[0], f"{type(e).__name__}: {e}"))      # take the bucket down:
+                continue                             # logged like post_processing does (post_processing.py:82-104)
             out.append((item[0], item[1], confidence, ph_seq, ph_intervals, word_seq, word_intervals))
         bucket.clear()
 
@@ -70,6 +75,11 @@ class BatchedPredictor:
         out, bucket, cells = [], [], 0.0
         for item in dataset:
             wav_path, wav_length, features, ph_seq, word_seq, ph_idx_to_word_idx = item
+            try:
+                self.decoder._ids_of(ph_seq)         # unknown phoneme / bad id: this utterance only
+            except (KeyError, IndexError) as e:
+                self.error_log.append((wav_path, f"{type(e).__name__}: {e}"))
+                continue
             y = self.forward(features)
             if isinstance(y, (tuple, list)):
                 frame, edge = y[0], y[1]

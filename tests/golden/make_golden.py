@@ -68,6 +68,22 @@ def main():
 
         dec._decode = spy
         r = dec.decode(frame, edge, ctc, wav_length, ph_seq, word_seq, ph2w)
+        # validation-time consumers (forced_alignment.py:413-414): the seven arguments plot() hands to
+        # tools.plot.plot_for_valid (ad:152-168), captured with a stand-in for the matplotlib function
+        import tools.alignment_decoder as ref_mod
+        import torch
+        plot_args = {}
+
+        def fake_plot(*a, _p=plot_args):
+            _p["args"] = a
+            return "figure"
+
+        real_plot, ref_mod.plot_for_valid = ref_mod.plot_for_valid, fake_plot
+        try:
+            n_fr = dec.ph_frame_pred.shape[0]
+            assert dec.plot(torch.zeros(1, 8, n_fr)) == "figure"
+        finally:
+            ref_mod.plot_for_valid = real_plot
         pre = f"{name}/"
         out[pre + "frame"] = frame[0].numpy()
         out[pre + "edge"] = edge[0].numpy()
@@ -83,6 +99,13 @@ def main():
         out[pre + "ph_idx_seq"] = dec.ph_idx_seq.astype(np.int64)
         out[pre + "ph_time_int"] = dec.ph_time_int_pred.astype(np.int64)
         out[pre + "frame_confidence"] = dec.frame_confidence.astype(np.float32)
+        if T <= 64 or name in ("c1_planted", "wavlen_trim"):      # [T, V] f32: kept for the small cases only
+            out[pre + "ph_frame_pred"] = dec.ph_frame_pred.astype(np.float32)     # ad:56-59,73
+        a = plot_args["args"]
+        out[pre + "plot_ph_seq"] = np.asarray(a[1]).astype("U")
+        out[pre + "plot_ph_intervals_int"] = np.asarray(a[2]).astype(np.int32)
+        out[pre + "plot_ph_idx_frame"] = np.asarray(a[5]).astype(np.int64)
+        out[pre + "plot_ph_frame_prob_sum"] = np.asarray(a[4], dtype=np.float64).sum(axis=0)   # [S]: a digest of [T, S]
         meta.append(dict(name=name, T=T, S=S, V=V, style=style, planted=planted, hop=hop, sr=sr,
                          wav_length=wav_length, ph_seq=ph_seq, word_seq=word_seq,
                          ph_idx_to_word_idx=[int(x) for x in ph2w]))

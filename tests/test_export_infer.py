@@ -92,6 +92,23 @@ def test_batched_predictor_equals_per_utterance_decode():
         assert g[0] == w[0] and g[1] == w[1] and g[2] == w[2]
         assert list(g[3]) == list(w[3]) and list(g[5]) == list(w[5])
         assert np.array_equal(g[4], w[4]) and np.array_equal(g[6], w[6])
+    # ... and against the ORACLE: the reference's own arithmetic (CPU torch softmax + the NumPy restatement of
+    # decode(), wav-length trimming and SP filter / word merge included) on the logits the network produced
+    from oracle import hfa_oracle_np as onp
+    with torch.no_grad():
+        for g, (wav_path, wl, k, ph, wd, p2w) in zip(got, dataset):
+            frame, edge = split_head(forward(k))
+            exp = onp.decode(vocab, synth.MELSPEC_50FPS, frame.float().cpu(), edge.float().cpu(), None, wl, ph, wd, p2w)
+            assert list(g[3]) == list(exp[0]) and list(g[5]) == list(exp[2]), wav_path
+            np.testing.assert_allclose(g[4], exp[1], rtol=0, atol=1e-7)
+            np.testing.assert_allclose(g[6], exp[3], rtol=0, atol=1e-7)
+            np.testing.assert_allclose(g[2], exp[4], rtol=1e-4)
+    # one unknown phoneme must cost one utterance, not the bucket
+    bad = list(dataset[1])
+    bad[3] = ["SP", "no-such-phoneme", "SP"]
+    pred2 = BatchedPredictor(forward, dec, bucket_utts=4)
+    got2 = pred2.predict([dataset[0], tuple(bad), dataset[2]])
+    assert len(got2) == 2 and len(pred2.error_log) == 1 and "KeyError" in pred2.error_log[0][1]
     res_g, log_g = post_processing([list(x) for x in got])
     res_w, log_w = post_processing([list(x) for x in want])
     assert not log_g and not log_w

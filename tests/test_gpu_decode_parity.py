@@ -142,6 +142,41 @@ def test_decode_matches_reference_golden(golden, name):
         assert np.isnan(conf)
     np.testing.assert_allclose(dec.edge_prob, c["edge_prob"], atol=5e-7)
     assert dec.ph_frame_pred.shape == (c["prob_log"].shape[0], m["V"])
+    assert dec.ph_frame_pred.dtype == np.float32
+    if "ph_frame_pred" in c:                          # ad:56-59,73: the masked softmax, values this time
+        np.testing.assert_allclose(dec.ph_frame_pred, c["ph_frame_pred"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dec.ph_frame_pred.sum(axis=1), 1.0, rtol=1e-5)
+    # plot() (ad:152-168, called by validation_step, forced_alignment.py:414): the seven arguments it hands to
+    # tools.plot.plot_for_valid must be the reference's -- captured with a stand-in for the matplotlib function
+    import sys
+    import types
+    got = {}
+    fake = types.ModuleType("tools.plot")
+    fake.plot_for_valid = lambda *a: got.setdefault("args", a) and "figure"
+    saved = {k: sys.modules.get(k) for k in ("tools", "tools.plot")}
+    sys.modules["tools"] = types.ModuleType("tools")
+    sys.modules["tools.plot"] = fake
+    try:
+        T_used = dec.ph_frame_pred.shape[0]
+        mel = torch.arange(8 * T_used, dtype=torch.float32).reshape(1, 8, T_used)
+        assert dec.plot(mel.cuda()) == "figure"
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    a = got["args"]
+    assert len(a) == 7
+    assert isinstance(a[0], np.ndarray) and np.array_equal(a[0], mel.numpy())              # melspec.cpu().numpy()
+    assert list(a[1]) == list(c["plot_ph_seq"])                                             # ph_pred_seq
+    assert np.array_equal(np.asarray(a[2]), c["plot_ph_intervals_int"]) and np.asarray(a[2]).dtype == np.int32
+    fin = np.isfinite(c["frame_confidence"])
+    np.testing.assert_allclose(a[3][fin], c["frame_confidence"][fin], rtol=2e-4, atol=1e-12)
+    assert a[4].shape == (T_used, len(m["ph_seq"]))                                         # ph_frame_pred[:, ph_seq_id]
+    np.testing.assert_allclose(np.asarray(a[4], dtype=np.float64).sum(axis=0), c["plot_ph_frame_prob_sum"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(np.asarray(a[5]), c["plot_ph_idx_frame"])                         # per-frame state index
+    np.testing.assert_allclose(a[6], c["edge_prob"], atol=5e-7)
 
 
 def test_decode_batch_c2_sized_vs_oracle():
