@@ -489,14 +489,14 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 if (keep_dp && !(hybrid && which == 0)) {
                     p->utt[b].dp_off = p->dp_store_elems;
                     // bands: one [T][32 k] block per band; strips: one 128-byte row per iteration
-                    p->dp_store_elems += sd > 0 ? (int64_t)nb * hfa_skew_blocks(sd, p->utt[b].T) * 512
+                    p->dp_store_elems += sd > 0 ? (int64_t)nb * hfa_skew_blocks(sd, p->utt[b].T) * HFA_SKEW_BLK * 32
                                                 : (int64_t)nb * p->utt[b].T * 32 * k;
                 }
                 for (int j = 0; j < nb; ++j) {
                     const bool has_right = j + 1 < nb;
                     p->band_items.push_back(HfaBandItem{b, j, has_right ? p->band_xchg_elems : 0});
                     // exchange slots (16 bytes each): bands 32 states x 2 per tile, strips one per frame
-                    if (has_right) p->band_xchg_elems += sd > 0 ? tiles * 16 : tiles * 64;
+                    if (has_right) p->band_xchg_elems += sd > 0 ? (tiles + 1) / 2 * 32 : tiles * 64;
                 }
             }
             p->band_count[which] = (int32_t)p->band_items.size() - p->band_begin[which];
@@ -693,7 +693,8 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
             if (m.status != 0 || m.tmap < 0) continue;
             const cuuint64_t dims[2] = {(cuuint64_t)m.Sp, (cuuint64_t)m.T};
             const cuuint64_t pitch[1] = {(cuuint64_t)m.Sp * 4};
-            const cuuint32_t box[2] = {(cuuint32_t)(m.skew_d > 0 ? HFA_SKEW_BOX : 32 * m.band_k), (cuuint32_t)HFA_TILE_T};
+            const cuuint32_t box[2] = {(cuuint32_t)(m.skew_d > 0 ? HFA_SKEW_BOX : 32 * m.band_k),
+                                       (cuuint32_t)(m.skew_d > 0 ? HFA_SKEW_BLK : HFA_TILE_T)};
             const cuuint32_t estr[2] = {1, 1};
             void *base = static_cast<unsigned char *>(workspace) + p->o_emis + m.emis_off * 4;
             const CUresult r = tensor_map_encoder()(&maps[(size_t)m.tmap], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base,

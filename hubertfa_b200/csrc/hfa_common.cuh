@@ -101,20 +101,24 @@ __host__ __device__ __forceinline__ int64_t hfa_dp_store_index(int K, int T, int
 // advance scores of the left strip's last two states, lanes 2..31 own states 30 w + 2 .. 30 w + 31.
 #define HFA_SKEW_OWN 30
 #define HFA_SKEW_BOX 36          // columns of its TMA box: the box starts at (30 w) & ~3, a 16-byte boundary
+#define HFA_SKEW_BLK 32          // frames per block (TMA tile rows, exchange batch, dp staging tile): 16 or 32
 __host__ __device__ __forceinline__ int hfa_skew_strips(int Sp)
 {
     return Sp <= 32 ? 1 : 1 + (Sp - 32 + HFA_SKEW_OWN - 1) / HFA_SKEW_OWN;
 }
-// 16-iteration blocks a strip runs: lane p handles frame t at iteration t + p D, the last lane finishes
-// frame T-1 at iteration T - 1 + 31 D
-__host__ __device__ __forceinline__ int hfa_skew_blocks(int D, int T) { return (T + 31 * D + 15) >> 4; }
+// blocks of HFA_SKEW_BLK iterations a strip runs: lane p handles frame t at iteration t + p D, the last
+// lane finishes frame T-1 at iteration T - 1 + 31 D
+__host__ __device__ __forceinline__ int hfa_skew_blocks(int D, int T)
+{
+    return (T + 31 * D + HFA_SKEW_BLK - 1) / HFA_SKEW_BLK;
+}
 // The kept dp of a skewed pass: every strip stores what its 32 lanes hold after each iteration, one
 // 128-byte row per iteration (so dp[t][s] sits at row t + p D of its strip, p = lane of state s).
 __host__ __device__ __forceinline__ int64_t hfa_skew_dp_index(int D, int T, int t, int s)
 {
     const int w = (s < 32) ? 0 : 1 + (s - 32) / HFA_SKEW_OWN;
     const int p = s - HFA_SKEW_OWN * w;
-    return ((int64_t)w * hfa_skew_blocks(D, T) * 16 + t + p * D) * 32 + p;
+    return ((int64_t)w * hfa_skew_blocks(D, T) * HFA_SKEW_BLK + t + p * D) * 32 + p;
 }
 
 // ---------------------------------------------------------------------------------------------

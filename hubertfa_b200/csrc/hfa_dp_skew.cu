@@ -216,18 +216,23 @@ __device__ __forceinline__ void sk_select_guarded(float up1, float stay, float u
 }
 
 constexpr int SK_BOXW = HFA_SKEW_BOX;                // columns of an emission tile in shared memory
+constexpr int BLK = HFA_SKEW_BLK;                    // iterations (= frames per lane) per block: one TMA tile,
+                                                     // one exchange batch, one dp staging tile, BLK / 16 backpointer words
 constexpr uint32_t SK_ROW_B = SK_BOXW * 4u;          // 144-byte rows
-constexpr uint32_t SK_STG_B = 16u * SK_ROW_B;        // 2304 bytes per stage (a multiple of 128)
+constexpr uint32_t SK_STG_B = BLK * SK_ROW_B;        // bytes per stage (a multiple of 128)
+constexpr uint32_t SK_EDGE_B = BLK * 8u;             // edge pairs of a stage
+constexpr uint32_t SK_DPST_B = BLK * 128u;           // one dp staging tile
+constexpr uint32_t SK_PUB_B = (2 * BLK + BLK + 32) * 4u;   // adv31 [BLK], adv30 [BLK], scratch [BLK + 32]
 constexpr int SK_LOOK = 3;                           // operands are loaded this many iterations ahead
+static_assert(BLK == 16 || BLK == 32, "a block is one or two backpointer words long");
 
 // shared-memory map (byte offsets from the 128-byte aligned base)
 template <int NSTG> struct SkSmem {
-    static constexpr uint32_t TILE = 0;                                   // [(NSTG + 1) x 16][36] f32 (+1: mirror of stage 0)
-    static constexpr uint32_t EDGE = TILE + (NSTG + 1) * SK_STG_B;        // [(NSTG + 1) x 16] float2
-    static constexpr uint32_t DPST = EDGE + (NSTG + 1) * 16 * 8;          // 2 x [16][32] f32: kept-dp staging
-    static constexpr uint32_t FEED = DPST + 2 * 2048;                     // [32][36] f32: ghost feeds, rows like a tile
-    static constexpr uint32_t PUB = FEED + 32 * SK_ROW_B;                 // 2 x {adv31 [16], adv30 [16], scratch [48]}
-    static constexpr uint32_t FULL = PUB + 2 * 80 * 4;                    // NSTG mbarriers
+    static constexpr uint32_t TILE = 0;                                   // [(NSTG + 1) x BLK][36] f32 (+1: mirror of stage 0)
+    static constexpr uint32_t EDGE = TILE + (NSTG + 1) * SK_STG_B;        // [(NSTG + 1) x BLK] float2
+    static constexpr uint32_t DPST = EDGE + (NSTG + 1) * SK_EDGE_B;       // 2 x [BLK][32] f32: kept-dp staging
+    static constexpr uint32_t PUB = DPST + 2 * SK_DPST_B;                 // 2 x publication staging
+    static constexpr uint32_t FULL = PUB + 2 * SK_PUB_B;                  // NSTG mbarriers
     static constexpr uint32_t SLOT = FULL + NSTG * 8;                     // work-item ticket
     static constexpr uint32_t BYTES = SLOT + 16;
 };
@@ -237,8 +242,8 @@ __global__ void __launch_bounds__(32)
 hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict__ dp_dump, int force_slow)
 {
     using SM = SkSmem<NSTG>;
-    constexpr int R = NSTG * 16;                    // ring rows
-    constexpr int Q = (31 * D + 15) / 16;           // tiles behind the newest one that lanes still read
+    constexpr int R = NSTG * BLK;                   // ring rows
+    constexpr int Q = (31 * D + BLK - 1) / BLK;     // tiles behind the newest one that lanes still read
     constexpr int PF = NSTG - 1 - Q;                // tiles fetched ahead of the newest one in use
     static_assert(D >= 2, "advance scores must be at least two iterations old when they are consumed");
     static_assert(PF >= 1, "ring too small for this skew");
@@ -287,21 +292,24 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     const bool seeded = !ghost && (s == 0 || (s == 1 && lead_sp));
     const float cap1 = (s == 0) ? NEG : POS;                   // nothing to the left of state 0
 
-    // tile i -> stage st (= i % NSTG, kept as a running counter); executed by ONE elected lane
+    // tile i -> stage st (= i % NSTG, kept as a running counter); executed by ONE elected lane.  The edge
+    // pairs of an utterance are padded to a multiple of 16 frames: the last copy of a 32-frame block may be short.
+    const int edge_len = (T + 15) & ~15;
     auto issue = [&](int i, int st) {
-        const int t0 = i * 16;
+        const int t0 = i * BLK;
         const uint32_t bar = sm0 + SM::FULL + 8u * (uint32_t)st;
         if (t0 >= T) {                                         // nothing to fetch: complete the phase
             sk_mbar_arrive(bar);
             return;
         }
-        const uint32_t bytes = SK_STG_B + 128u;
+        const uint32_t ebytes = (uint32_t)min(BLK, edge_len - t0) * 8u;
+        const uint32_t bytes = SK_STG_B + ebytes;
         sk_mbar_expect_tx(bar, st == 0 ? 2u * bytes : bytes);
         sk_tensor_load_2d(sm0 + SM::TILE + (uint32_t)st * SK_STG_B, tmap, c0 & ~3, t0, bar);
-        sk_bulk_load(sm0 + SM::EDGE + (uint32_t)st * 128u, g_edge + t0, 128u, bar);
+        sk_bulk_load(sm0 + SM::EDGE + (uint32_t)st * SK_EDGE_B, g_edge + t0, ebytes, bar);
         if (st == 0) {                                         // the mirror behind the last stage
             sk_tensor_load_2d(sm0 + SM::TILE + (uint32_t)NSTG * SK_STG_B, tmap, c0 & ~3, t0, bar);
-            sk_bulk_load(sm0 + SM::EDGE + (uint32_t)NSTG * 128u, g_edge + t0, 128u, bar);
+            sk_bulk_load(sm0 + SM::EDGE + (uint32_t)NSTG * SK_EDGE_B, g_edge + t0, ebytes, bar);
         }
     };
     static_assert(PF + 1 <= NSTG, "prologue fills distinct stages");
@@ -321,14 +329,13 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
 #pragma unroll
     for (int i = 0; i < 2 * D; ++i) q2[i] = NEG;
 
-    // per-lane ring position of the first row of the current block: (16 j - lane D) mod R
+    // per-lane ring position of the first row of the current block: (BLK j - lane D) mod R
     int u_row = ((-lane * D) % R + R) % R;
-    // a ghost lane's "emission" is its feed: rows like a tile's, two halves of 16 used alternately
+    // (a ghost lane's "emission" is the left strip's advance score: written over its column of the tile, below)
     const uint32_t tile_sa = sm0 + SM::TILE + 4u * (uint32_t)(lane + (c0 & 3));
-    const uint32_t feed_sa = sm0 + SM::FEED + 4u * (uint32_t)lane;
     const uint32_t edge_sa = sm0 + SM::EDGE;
     const uint32_t dpst_sa = sm0 + SM::DPST + 4u * (uint32_t)lane;
-    // backpointer bookkeeping: the 16 frames of a block straddle two 16-frame rows
+    // backpointer bookkeeping: the 16 frames of a half-block straddle two 16-frame rows
     const int o_res = (lane * D) & 15;
     const int q_rows = (lane * D + 15) >> 4;
     const uint32_t m16 = o_res ? ((0xffffu << (16 - o_res)) & 0xffffu) : 0xffffu;
@@ -340,33 +347,40 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     // publication staging: every iteration each lane parks its advance score at [its base + 4 k]; only the
     // rows of lanes 31 and 30 are read back (the other lanes write to a scratch area, one column each)
     const uint32_t pub_sa = sm0 + SM::PUB +
-                            ((has_right && lane == 31) ? 0u : (has_right && lane == 30) ? 64u : 128u + 4u * (uint32_t)lane);
-    // running pointers of the per-block stores: this lane's backpointer word of row j - q_rows, and the
-    // exchange word it publishes (lanes 0-15: adv31 of frame 16 j + lane - 31 D, lanes 16-31: adv30 of frame
-    // 16 j + lane - 16 - 30 D)
+                            ((has_right && lane == 31) ? 0u : (has_right && lane == 30) ? 4u * BLK
+                                                                                        : 8u * BLK + 4u * (uint32_t)lane);
+    // running pointer of this lane's backpointer word of row (16-frame half-block index) - q_rows
     uint32_t *bp_ptr = g_bp + (int64_t)(-q_rows) * Sp + s;
     int bp_row = -q_rows;
-    int pub_t = (lane & 15) - (31 - (lane >> 4)) * D;
-    unsigned long long *pub_ptr = reinterpret_cast<unsigned long long *>(my_x + pub_t) + (lane >> 4);
-    const uint32_t pubrd_sa = sm0 + SM::PUB + 4u * (uint32_t)(16 * (lane >> 4) + (lane & 15));
-    float *g_dp = (KEEP && m.dp_off >= 0) ? ws.dp_store + m.dp_off + (int64_t)w * NB * 512 : nullptr;
+    float *g_dp = (KEEP && m.dp_off >= 0) ? ws.dp_store + m.dp_off + (int64_t)w * NB * (BLK * 32) : nullptr;
 
     // exchange slots of the NEXT block, fetched one block early (the left strip is normally that far ahead)
     ulonglong2 xv_next = make_ulonglong2(0ull, 0ull);
-    auto slot_needed = [&](int jj) { const int t = 16 * jj + lane; return has_left && lane < 16 && t >= 1 && t < T; };
+    auto slot_needed = [&](int jj) { const int t = BLK * jj + lane; return has_left && lane < BLK && t >= 1 && t < T; };
     if (slot_needed(0)) xv_next = sk_ld_slot(left_x + lane);
+
+    // one 16-frame backpointer word: `bits` holds the first part of row bp_row (from the previous half-block),
+    // its last part is acc[hi_mask]; the rest of acc opens the next row
+    auto flush_bits = [&](uint32_t acc, bool all_valid) {
+        if (real && (all_valid || (bp_row >= 0 && bp_row < n_rows))) *bp_ptr = bits | (acc & hi_mask);
+        bits = acc & ~hi_mask;
+        bp_ptr += Sp;
+        ++bp_row;
+    };
 
     for (int j = 0; j < NB; ++j) {
         sk_mbar_wait(sm0 + SM::FULL + 8u * (uint32_t)st_wait, par_wait);
+        const int st_cur = st_wait;                            // stage that holds frames BLK j .. BLK j + BLK - 1
         if (++st_wait == NSTG) {
             st_wait = 0;
             par_wait ^= 1u;
         }
 
         if (has_left) {
-            // the left strip's advance scores for frames 16 j .. 16 j + 15 (ghost lane 0 is at frame n,
-            // ghost lane 1 at frame n - D: its feed is stored D rows late so both read row n)
-            const int t = 16 * j + lane;
+            // The left strip's advance scores for frames BLK j .. BLK j + BLK - 1 go where the ghost lanes look for
+            // their "emission": ghost lane 0 (the left strip's state 30) reads column c0 of row t of the tile,
+            // ghost lane 1 (state 31) column c0 + 1 -- the emissions TMA put there are of no use to anybody.
+            const int t = BLK * j + lane;
             const bool need = slot_needed(j);
             ulonglong2 *src = const_cast<ulonglong2 *>(left_x) + t;
             const uint32_t tag = (uint32_t)t + 1u;
@@ -378,27 +392,36 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                 if (++spins > (1u << 26)) __trap();
                 if (!ok) v = sk_ld_slot(src);
             }
-            if (slot_needed(j + 1)) xv_next = sk_ld_slot(src + 16);            // consumed one block later
-            if (lane < 16) {
-                sk_sts_f32(sm0 + SM::FEED + (uint32_t)(t & 31) * SK_ROW_B, need ? __uint_as_float((uint32_t)v.y) : 0.0f);            // adv30(t)
-                sk_sts_f32(sm0 + SM::FEED + (uint32_t)((t + D) & 31) * SK_ROW_B + 4u, need ? __uint_as_float((uint32_t)v.x) : 0.0f); // adv31(t)
+            if (slot_needed(j + 1)) xv_next = sk_ld_slot(src + BLK);           // consumed one block later
+            if (lane < BLK) {
+                const float a30 = need ? __uint_as_float((uint32_t)v.y) : 0.0f;
+                const float a31 = need ? __uint_as_float((uint32_t)v.x) : 0.0f;
+                const uint32_t row_sa = sm0 + SM::TILE + (uint32_t)st_cur * SK_STG_B + (uint32_t)lane * SK_ROW_B +
+                                        4u * (uint32_t)(c0 & 3);
+                sk_sts_f32(row_sa, a30);
+                sk_sts_f32(row_sa + 4u, a31);
+                if (st_cur == 0) {                                             // and its mirror
+                    sk_sts_f32(row_sa + (uint32_t)NSTG * SK_STG_B, a30);
+                    sk_sts_f32(row_sa + (uint32_t)NSTG * SK_STG_B + 4u, a31);
+                }
                 if (need) sk_st_slot(src, 0ull, 0ull);                         // leave the table clean
             }
+            hfa_fence_async_smem();       // generic writes into a stage the TMA engine will refill later
             __syncwarp();
         }
-        const uint32_t e_sa = ghost ? feed_sa + (uint32_t)(j & 1) * (16u * SK_ROW_B) : tile_sa + (uint32_t)u_row * SK_ROW_B;
+        const uint32_t e_sa = tile_sa + (uint32_t)u_row * SK_ROW_B;
         const uint32_t d_sa = edge_sa + (uint32_t)u_row * 8u;
-        const uint32_t k_sa = dpst_sa + (uint32_t)(j & 1) * 2048u;
-        const uint32_t p_sa = pub_sa + (uint32_t)(j & 1) * 320u;
-        // all 32 lanes inside frames 1 .. T-1 for all 16 iterations?
-        const bool steady = (16 * j - 31 * D >= 1) && (16 * j + 15 <= T - 1);
-        uint32_t acc = 0;                                      // this block's backpointer bits, by frame residue
+        const uint32_t k_sa = dpst_sa + (uint32_t)(j & 1) * SK_DPST_B;
+        const uint32_t p_sa = pub_sa + (uint32_t)(j & 1) * SK_PUB_B;
+        // all 32 lanes inside frames 1 .. T-1 for all BLK iterations?
+        const bool steady = (BLK * j - 31 * D >= 1) && (BLK * j + BLK - 1 <= T - 1);
 
         if ((j == 0 && !has_left) || force_slow) {
             // ---------------- the block that seeds frame 0 (:250-254): rolled, one frame at a time ----------------
+            uint32_t acc = 0;
 #pragma unroll 1
-            for (int k = 0; k < 16; ++k) {
-                const int t = 16 * j + k - lane * D;
+            for (int k = 0; k < BLK; ++k) {
+                const int t = BLK * j + k - lane * D;
                 const bool live = (t >= 1) && (t < T);
                 const float e = sk_lds_f32(e_sa + SK_ROW_B * k);
                 const float2 ed = sk_lds_f2(d_sa + 8u * k);
@@ -434,27 +457,31 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                 if (DUMP) {
                     if (!ghost && s < S && t >= 0 && t < T) dp_dump[m.cell_off + (int64_t)t * S + s] = dp;
                 }
+                if ((k & 15) == 15) {
+                    flush_bits(acc, false);
+                    acc = 0;
+                }
             }
         } else {
-            // ---------------- 16 iterations unrolled; `steady`: no lane needs a guard ----------------
+            // ---------------- BLK iterations unrolled; `steady`: no lane needs a guard ----------------
             // operands are fetched SK_LOOK iterations ahead, interleaved with the arithmetic
-            float ev[16];
-            float2 dv[16];
+            float ev[BLK];
+            float2 dv[BLK];
 #pragma unroll
             for (int k = 0; k < SK_LOOK; ++k) {
                 ev[k] = sk_lds_f32(e_sa + SK_ROW_B * k);
                 dv[k] = sk_lds_f2(d_sa + 8u * k);
             }
-            float r1[16 + D], r2[16 + 2 * D];
+            float r1[BLK + D], r2[BLK + 2 * D];
 #pragma unroll
             for (int i = 0; i < D; ++i) r1[i] = q1[i];
 #pragma unroll
             for (int i = 0; i < 2 * D; ++i) r2[i] = q2[i];
-            uint32_t mr = mrot0;
+            uint32_t mr = mrot0, acc = 0;
             if (!DUMP && steady) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k + SK_LOOK < 16) {
+                for (int k = 0; k < BLK; ++k) {
+                    if (k + SK_LOOK < BLK) {
                         ev[k + SK_LOOK] = sk_lds_f32(e_sa + SK_ROW_B * (k + SK_LOOK));
                         dv[k + SK_LOOK] = sk_lds_f2(d_sa + 8u * (k + SK_LOOK));
                     }
@@ -470,12 +497,16 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                     sk_select(r1[k], stay, r2[k], pe, sp_hi, mr, dp, P, acc);
                     mr = __funnelshift_l(mr, mr, 1);
                     if (KEEP) sk_sts_f32(k_sa + 128u * k, dp);
+                    if ((k & 15) == 15) {
+                        flush_bits(acc, true);
+                        acc = 0;
+                    }
                 }
             } else {
-                const int tb = 16 * j - lane * D - 1;          // (frame of iteration 0) - 1
+                const int tb = BLK * j - lane * D - 1;         // (frame of iteration 0) - 1
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k + SK_LOOK < 16) {
+                for (int k = 0; k < BLK; ++k) {
+                    if (k + SK_LOOK < BLK) {
                         ev[k + SK_LOOK] = sk_lds_f32(e_sa + SK_ROW_B * (k + SK_LOOK));
                         dv[k + SK_LOOK] = sk_lds_f2(d_sa + 8u * (k + SK_LOOK));
                     }
@@ -496,47 +527,50 @@ hfa_dp_skew_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
                         const int t = tb + 1 + k;
                         if (!ghost && s < S && t >= 0 && t < T) dp_dump[m.cell_off + (int64_t)t * S + s] = dp;
                     }
+                    if ((k & 15) == 15) {
+                        flush_bits(acc, false);
+                        acc = 0;
+                    }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < D; ++i) q1[i] = r1[16 + i];
+            for (int i = 0; i < D; ++i) q1[i] = r1[BLK + i];
 #pragma unroll
-            for (int i = 0; i < 2 * D; ++i) q2[i] = r2[16 + i];
+            for (int i = 0; i < 2 * D; ++i) q2[i] = r2[BLK + i];
         }
-        // Backpointer words.  A lane's 16 frames of a block straddle two 16-frame rows: `bits` holds the
-        // first part of row j - q_rows (from the previous block), its last part is acc[hi_mask]; the rest
-        // of acc opens the next row.
-        if (real && bp_row >= 0 && bp_row < n_rows) *bp_ptr = bits | (acc & hi_mask);
-        bits = acc & ~hi_mask;
-        bp_ptr += Sp;
-        ++bp_row;
         if (KEEP) hfa_fence_async_smem();                      // this block's dp rows -> visible to the bulk store
         __syncwarp();                                          // every lane is done with this block's stage reads,
                                                                // staging writes and the stage refilled below
         if (has_right) {
-            // the 16 advance scores lanes 31 and 30 have parked: lanes 0-15 / 16-31 publish them, one tagged
-            // 64-bit word each (frames 1 .. T-1 only; the staging is double-buffered)
-            if (pub_t >= 1 && pub_t < T)
-                sk_st_word(pub_ptr, sk_pack(sk_lds_f32(pubrd_sa + (uint32_t)(j & 1) * 320u), (uint32_t)pub_t + 1u));
-            pub_t += 16;
-            pub_ptr += 32;                                     // 16 slots of two words
+            // the advance scores lanes 31 and 30 have parked: published as tagged 64-bit words, adv31 of frame
+            // BLK j + i - 31 D into .x, adv30 of frame BLK j + i - 30 D into .y (frames 1 .. T-1 only; the
+            // staging is double-buffered)
+#pragma unroll
+            for (int q = lane; q < 2 * BLK; q += 32) {
+                const int half = q / BLK, i = q % BLK;
+                const int t = BLK * j + i - (31 - half) * D;
+                if (steady || (t >= 1 && t < T))
+                    sk_st_word(reinterpret_cast<unsigned long long *>(my_x + t) + half,
+                               sk_pack(sk_lds_f32(sm0 + SM::PUB + (uint32_t)(j & 1) * SK_PUB_B + 4u * (uint32_t)q),
+                                       (uint32_t)t + 1u));
+            }
         }
         if (sk_elect_one()) {
             if (KEEP && g_dp != nullptr) {
-                // the block's 16 rows of dp leave as one bulk store; the staging tile written two blocks
+                // the block's rows of dp leave as one bulk store; the staging tile written two blocks
                 // ago must have been read out before the next block overwrites it
-                sk_bulk_store(g_dp + (int64_t)j * 512, sm0 + SM::DPST + (uint32_t)(j & 1) * 2048u, 2048u);
+                sk_bulk_store(g_dp + (int64_t)j * (BLK * 32), sm0 + SM::DPST + (uint32_t)(j & 1) * SK_DPST_B, SK_DPST_B);
                 hfa_bulk_commit();
                 sk_bulk_wait_read_1();
             }
             if (j + PF + 1 < NB) issue(j + PF + 1, st_issue);  // into the stage last read during this block
         }
         if (++st_issue == NSTG) st_issue = 0;
-        u_row += 16;
+        u_row += BLK;
         if (u_row >= R) u_row -= R;
     }
     // a lane whose frames end before the loop does carries the first part of one more row
-    if (real && o_res != 0 && NB - q_rows < n_rows) g_bp[(int64_t)(NB - q_rows) * Sp + s] = bits;
+    if (real && o_res != 0 && bp_row >= 0 && bp_row < n_rows) *bp_ptr = bits;
     // nothing touched dp after frame T-1: it is dp[T-1][s] (:269-272 needs the last two states)
     if (!ghost) {
         if (s == S - 1) ws.dp_last[2 * u] = dp;
@@ -581,7 +615,8 @@ cudaError_t hfa_launch_dp_skew(const HfaLaunchCtx &c, int d, int item_begin, int
     // HFA_SKEW_SLOW=1: every block through the guarded body (A/B against the unrolled steady state)
     const char *sl = getenv("HFA_SKEW_SLOW");
     const int force_slow = (sl && sl[0] == '1') ? 1 : 0;
-    if (d == 2) return launch_skew_d<2, 12>(c, item_begin, n_items, ticket, keep_dp, dp_dump, force_slow);
-    if (d == 3) return launch_skew_d<3, 12>(c, item_begin, n_items, ticket, keep_dp, dp_dump, force_slow);
+    constexpr int NS = HFA_SKEW_BLK == 32 ? 5 : 12;            // a ring of 160 / 192 frames
+    if (d == 2) return launch_skew_d<2, NS>(c, item_begin, n_items, ticket, keep_dp, dp_dump, force_slow);
+    if (d == 3) return launch_skew_d<3, NS>(c, item_begin, n_items, ticket, keep_dp, dp_dump, force_slow);
     return cudaErrorInvalidValue;
 }
