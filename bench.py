@@ -52,7 +52,9 @@ WORKLOADS = {
     "m1024": (1024, 63, (5, 30), (20, 150), "1024 utterances, 5-30 s, 20-150 phonemes, V=63"),
     "m2048": (2048, 63, (5, 30), (20, 150), "2048 utterances, 5-30 s, 20-150 phonemes, V=63"),
 }
-CORPUS_CHUNK_CELLS = 150_000_000     # workspace bound of a corpus chunk (~2000 utterances, ~0.7 GB)
+CORPUS_CHUNK_CELLS = 600_000_000     # workspace bound of a corpus chunk (~8000 utterances, ~5.5 GB): measured on
+                                     # one B200, 32768 utterances: 9.44 / 8.72 / 8.58 / 8.63 ms per pass with
+                                     # chunks of 150M / 300M / 600M / 1200M cells (tools/gpu/r2_chunks2.sh)
 
 
 def workload_shapes(name: str, seed: int, corpus: int = 0):
@@ -192,7 +194,8 @@ def run_reference(args, rank, world):
     from oracle import c_oracle as oc
     name = args.workload or ("c2" if args.gpus <= 1 else "c5")
     T, S, V, desc = workload_shapes(name, synth.SEED0, args.corpus)
-    ids_list = synth.make_ids_batch(T, S, V, seed=synth.SEED0)
+    ids_list = (synth.make_ids_corpus(S, V, seed=synth.SEED0) if name == "c5"
+                else synth.make_ids_batch(T, S, V, seed=synth.SEED0))
     cfg = make_config(name, desc, T, S, args.gpus)
     sample = "the full batch"
     if name == "c5":      # bounded sample of the corpus: its first 2048 utterances
@@ -267,7 +270,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--corpus", type=int, default=16384, help="utterances of the corpus workload (c5)")
+    ap.add_argument("--corpus", type=int, default=100000, help="utterances of the corpus workload (c5)")
+    ap.add_argument("--corpus-chunk-cells", type=int, default=0, help="DP cells per corpus chunk (0: automatic)")
+    ap.add_argument("--corpus-streams", type=int, default=0, help="streams the corpus chunks alternate over (0: default)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg of the corpus arm")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra passes (c4 roofline, corpus, replicas)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of one graph replay")
@@ -532,8 +538,8 @@ def main():
         """ranks = 1: this process alone runs the whole corpus (the strong-scaling reference)."""
         from hubertfa_b200.corpus import CorpusAligner, CorpusPlan, SharedHostBuffer, all_status_ok, read_results
         T, S, V, desc = workload_shapes("c5", synth.SEED0, n_utt)
-        ids_list = synth.make_ids_batch(T, S, V, seed=synth.SEED0)
-        cp = CorpusPlan(T, S, ids_list, V, synth.FRAME_SECONDS, ranks, CORPUS_CHUNK_CELLS)
+        ids_list = synth.make_ids_corpus(S, V, seed=synth.SEED0)
+        cp = CorpusPlan(T, S, ids_list, V, synth.FRAME_SECONDS, ranks, args.corpus_chunk_cells or CORPUS_CHUNK_CELLS)
         row_off = np.concatenate([[0], np.cumsum(T.astype(np.int64))])
         # the SAME logits on every rank: the whole corpus from one seeded device generator (3.7 GB at the
         # default size); a rank only ever reads its own utterances' rows
@@ -555,7 +561,7 @@ def main():
                 host = SharedHostBuffer(name, cp.total_result_bytes, create=False)
         else:
             host = SharedHostBuffer(name, cp.total_result_bytes, create=True)
-        al = CorpusAligner(cp, my_rank, dev, head, row_off, host)
+        al = CorpusAligner(cp, my_rank, dev, head, row_off, host, n_streams=args.corpus_streams or 2)
 
         def sync_all():
             torch.cuda.synchronize()
@@ -582,6 +588,7 @@ def main():
             barrier()
         out = dict(cp=cp, T=T, S=S, V=V, desc=desc, ms=ms, clk=clk, launches=al.launches_per_pass * steps,
                    chunks=[len(c) for c in cp.chunks], d2h=int(sum(c["plan"].result_bytes for c in al.chunks)))
+        torch.cuda.synchronize()
         if my_rank == 0:
             out["ok"] = all_status_ok(cp, host)
             sample = np.unique(np.linspace(0, n_utt - 1, 24).astype(np.int64))
@@ -595,7 +602,10 @@ def main():
                 lambda j: (res[int(sample[j])]["ph_idx_seq"], res[int(sample[j])]["ph_time_int"]),
                 np.arange(len(sample)), synth.FRAME_SECONDS)
         e2e = None
-        if do_e2e:
+        al.close()
+        del al
+        torch.cuda.empty_cache()
+        if do_e2e and not args.no_e2e:
             # pinned host copy of this rank's rows -> device staging -> the same pass, every step
             mine = np.sort(cp.shards[my_rank])
             rows = torch.cat([torch.arange(row_off[b], row_off[b + 1]) for b in mine]).to(dev)
@@ -603,7 +613,7 @@ def main():
             stage = torch.empty_like(head[rows])
             my_off = np.zeros(n_utt, dtype=np.int64)
             my_off[mine] = np.concatenate([[0], np.cumsum(T[mine].astype(np.int64))])[:-1]
-            al2 = CorpusAligner(cp, my_rank, dev, stage, my_off, host)
+            al2 = CorpusAligner(cp, my_rank, dev, stage, my_off, host, n_streams=args.corpus_streams or 2)
             n_piece = 8
             cuts = [int(x) for x in np.linspace(0, stage.shape[0], n_piece + 1)]
 
@@ -647,7 +657,6 @@ def main():
             al2.close()
             if multi:
                 barrier()
-        al.close()
         out["e2e"] = e2e
         out["host"] = host
         return out

@@ -80,8 +80,13 @@ class CorpusPlan:
         # chunks[r] = list of corpus-index arrays; inside a chunk longest utterance first (collation order)
         self.chunks = []
         for shard in self.shards:
+            # equal-sized chunks (a small remainder chunk would leave one of the two streams idle): as few as the
+            # workspace bound allows, utterances dealt round-robin from the longest down so that every chunk gets
+            # the same mix of lengths; inside a chunk longest first
             order = shard[np.argsort(-self.T[shard].astype(np.int64), kind="stable")]
-            self.chunks.append([order[c] for c in sharding.chunk_by_bytes(self.T[order], self.S[order], max_cells)])
+            cells = int((self.T[shard].astype(np.int64) * self.S[shard]).sum())
+            n_chunks = max(1, -(-cells // max(int(max_cells), 1)))
+            self.chunks.append([order[k::n_chunks] for k in range(n_chunks) if len(order[k::n_chunks])])
         # result blob of a chunk: the HfaResultLayout of its plan; its size follows from (n_utt, sum S) alone
         self.blob_off, off = [], 0
         for r in range(world):
@@ -108,7 +113,7 @@ class CorpusAligner:
     """One rank's share of a CorpusPlan: persistent per-chunk plans / workspaces, ``run()`` = one pass."""
 
     def __init__(self, cp: CorpusPlan, rank: int, device, head: torch.Tensor, row_off: np.ndarray,
-                 host: SharedHostBuffer, frame_col: int = 2, edge_col: int = 0):
+                 host: SharedHostBuffer, frame_col: int = 2, edge_col: int = 0, n_streams: int = 2):
         """head: [sum T, W] logits of the WHOLE corpus (or at least of this rank's utterances at their corpus
         rows) on ``device``; row_off[b] = first row of utterance b."""
         self.cp, self.rank, self.dev, self.host = cp, rank, torch.device(device), host
@@ -116,7 +121,7 @@ class CorpusAligner:
         self.chunks = []
         W, esz, base = head.shape[1], head.element_size(), head.data_ptr()
         with torch.cuda.device(self.dev):
-            self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+            self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(int(n_streams), 1))]
             for k, idx in enumerate(cp.chunks[rank]):
                 ids = np.concatenate([cp.ids_list[i] for i in idx]) if len(idx) else np.zeros(0, np.int32)
                 plan = ops.AlignPlan(cp.T[idx], cp.S[idx], ids, cp.vocab_size, cp.frame_length)
@@ -143,7 +148,7 @@ class CorpusAligner:
         for st in self.streams:
             st.wait_stream(cur)
         for k, c in enumerate(self.chunks):
-            st = self.streams[k & 1]
+            st = self.streams[k % len(self.streams)]
             with torch.cuda.stream(st):
                 ops.align_batch(c["ws"], c["plan"].handle, self.dtype, c["res"], None)
                 c["host"].copy_(c["res"][:c["plan"].result_bytes], non_blocking=True)

@@ -353,8 +353,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         // utterance becomes several 2-states-per-lane warps on different SMs.  Big batches keep
         // one warp per utterance (no redundant halo work).
         //   HFA_LATENCY_MODE = 0: never band (S <= 256) | 2: always band | 1: the older multi-warp
-        //   CTA kernel with a barrier per frame | unset: band when the batch has <= HFA_BAND_MAX
-        //   (default 1184 = 8 per SM) band warps.   HFA_BIG_KERNEL = cta | band, HFA_BIG_K = 2|4|8.
+        //   CTA kernel with a barrier per frame | unset: strips / bands when the batch needs <= HFA_BAND_MAX
+        //   (default 3072) of them.   HFA_BIG_KERNEL = cta | band, HFA_BIG_K = 2|4|8.
         // Latency-regime kernel: the skewed wavefront (default; needs the TMA tensor maps) or the halo bands.
         //   HFA_LAT_KERNEL = skew | band,   HFA_SKEW_D = 2 | 3 (frames of skew per state)
         int skew_d = 2;
@@ -366,7 +366,10 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             const int w = 32 * k, own = w - 32, sp = p->utt[b].Sp;
             return sp <= w ? 1 : (sp - 32 + own - 1) / own;
         };
-        int64_t band_max = 1184;
+        // measured crossover (profiles/r2_routing_crossover.json, B200): strips win for 256 / 512 utterances
+        // (820 / 1674 strips: 0.22 vs 0.44 ms, 0.33 vs 0.48 ms per step), tie at 1024 (3310 strips: 0.550 vs
+        // 0.553 ms), one warp per utterance wins at 2048 (6582 strips: 1.03 vs 0.73 ms)
+        int64_t band_max = 3072;
         if (const char *e = std::getenv("HFA_BAND_MAX")) band_max = std::atoll(e);
         int lat_mode = -1;
         if (const char *e = std::getenv("HFA_LATENCY_MODE")) lat_mode = e[0] - '0';

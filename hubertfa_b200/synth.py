@@ -111,3 +111,28 @@ def make_ids_batch(T, S, V: int, seed: int = SEED0, style: str = "dictionary"):
         ph_seq, _, _ = make_ph_seq(rng, int(s), V, style)
         out.append(np.array([0 if p == "SP" else int(p[1:]) for p in ph_seq], dtype=np.int32))
     return out
+
+
+def make_ids_corpus(S, V: int, seed: int = SEED0):
+    """``make_ids_batch`` for corpus sizes (100 000 utterances): dictionary-style sequences -- SP, then words of
+    1-2 phonemes each followed by SP, cut at S states (networks/g2p/dictionary_g2p.py:16-42) -- drawn with a few
+    vectorised numpy calls per utterance instead of one per phoneme.  Deterministic in (S, V, seed)."""
+    rng = np.random.default_rng(seed)
+    S = np.asarray(S, dtype=np.int64)
+    total = int(S.sum())
+    # one stream of (SP + word) units long enough for every utterance; an utterance takes the next units
+    wlen = rng.integers(1, 3, size=total + len(S)).astype(np.int64)          # phonemes per word: 1 or 2
+    phon = rng.integers(1, V, size=2 * total + 2 * len(S)).astype(np.int32)
+    out, wi, pi = [], 0, 0
+    for s in S:
+        s = int(s)
+        n_units = s                                   # more than enough units for s states
+        unit = wlen[wi:wi + n_units] + 1              # SP + word
+        start = np.concatenate([[0], np.cumsum(unit)[:-1]])
+        used = int(np.searchsorted(start, s, side="left"))
+        ids = phon[pi:pi + s].copy()
+        ids[start[:used]] = 0                         # the SP that opens every unit
+        out.append(ids)
+        wi += used
+        pi += s
+    return out
