@@ -81,12 +81,16 @@ class CorpusPlan:
         self.chunks = []
         for shard in self.shards:
             # equal-sized chunks (a small remainder chunk would leave one of the two streams idle): as few as the
-            # workspace bound allows, utterances dealt round-robin from the longest down so that every chunk gets
-            # the same mix of lengths; inside a chunk longest first
-            order = shard[np.argsort(-self.T[shard].astype(np.int64), kind="stable")]
+            # workspace bound allows, balanced by cost like the shards themselves; inside a chunk longest first
             cells = int((self.T[shard].astype(np.int64) * self.S[shard]).sum())
             n_chunks = max(1, -(-cells // max(int(max_cells), 1)))
-            self.chunks.append([order[k::n_chunks] for k in range(n_chunks) if len(order[k::n_chunks])])
+            parts = sharding.shard_by_cost(self.T[shard], self.S[shard], n_chunks)
+            chunks = []
+            for part in parts:
+                idx = shard[part]
+                if len(idx):
+                    chunks.append(idx[np.argsort(-self.T[idx].astype(np.int64), kind="stable")])
+            self.chunks.append(chunks)
         # result blob of a chunk: the HfaResultLayout of its plan; its size follows from (n_utt, sum S) alone
         self.blob_off, off = [], 0
         for r in range(world):
