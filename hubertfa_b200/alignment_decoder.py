@@ -126,6 +126,14 @@ class BatchAlignment:
 class AlignmentDecoder:
     """Same interface as the reference class (ad:8-168); compute runs on the current CUDA device."""
 
+    # How decode() / decode_batch() reach hfa_align_batch.  False (default): the C ABI is called directly
+    # through ctypes.  True: through the ``hfa::align_batch`` torch custom op (same entry point, same stream).
+    # Measured on B200, one T=500 / S=40 utterance per call (tools/time_decode.py): 0.40 ms per decode() through
+    # the op against 0.26 ms direct -- torch's Python custom-op dispatcher costs ~0.1 ms per call, more than the
+    # 0.064 ms the kernels take, and predict_step (forced_alignment.py:174-176) pays it once per utterance.
+    # The ops stay the interface for graph capture, the benchmark and the stage-level tests.
+    dispatch_through_torch_op = False
+
     def __init__(self, vocab, melspec_config, device=None):
         _lib.load()                           # fail at construction if the CUDA library is missing
         self.vocab = vocab
@@ -183,9 +191,8 @@ class AlignmentDecoder:
         S = np.array([len(i) for i in ids_list], dtype=np.int32)
         ids = np.concatenate(ids_list).astype(np.int32) if len(ids_list) else np.zeros(0, np.int32)
         plan = ops.AlignPlan(T, S, ids, self.vocab["vocab_size"], self.frame_length)
-        # Collation tables go through the plan's ctypes methods; the compute is ONE dispatch of the
-        # hfa::align_batch custom op (emission -> DP -> backtrace on the current stream).  Pinned result
-        # buffers are kept across calls (grow-only).
+        # One device context, the plan's tables and ONE hfa_align_batch call (emission -> DP -> backtrace on
+        # the current stream; see dispatch_through_torch_op).  Pinned result buffers are kept across calls.
         lib = _lib.load()
         n = len(frames)
         tabs = [np.fromiter((f.data_ptr() for f in frames), dtype=np.int64, count=n),
@@ -202,7 +209,11 @@ class AlignmentDecoder:
             sp, h, wp = int(stream.cuda_stream), plan.handle, ws.data_ptr()
             _lib.check(lib.hfa_plan_upload(h, wp, sp), "hfa_plan_upload")
             _lib.check(lib.hfa_set_inputs(h, wp, *[a.ctypes.data for a in tabs], sp), "hfa_set_inputs")
-            ops.align_batch(ws, h, ops.TORCH_TO_DTYPE[dtype], res, fc)
+            if self.dispatch_through_torch_op:
+                ops.align_batch(ws, h, ops.TORCH_TO_DTYPE[dtype], res, fc)
+            else:
+                _lib.check(lib.hfa_align_batch(h, wp, ops.TORCH_TO_DTYPE[dtype], res.data_ptr(),
+                                               fc.data_ptr() if fc is not None else None, sp), "hfa_align_batch")
             host = self._pinned("res", plan.result_bytes, torch.uint8)
             host.copy_(res, non_blocking=True)
             fc_host = None
@@ -271,11 +282,16 @@ class AlignmentDecoder:
         self.frame_confidence = fc.copy()
         self.final_score = np.float32(v["final_score"][0])
 
-        # ad:115-138: SP filter and word merge, the batch code path on a batch of one
-        is_sp = np.fromiter((p == "SP" for p in ph_seq), dtype=bool, count=len(ph_seq))
-        one = BatchAlignment(plan, v, [ph_seq], [word_seq], [ph_idx_to_word_idx], is_sp,
-                             np.asarray(ph_idx_to_word_idx, dtype=np.int64))
-        ph_seq_pred, ph_intervals_pred, word_seq_pred, word_intervals_pred, _ = one[0]
+        # ad:115-138 for one utterance: drop the segments labelled "SP", then merge runs of consecutive
+        # phonemes that belong to the same word into one [first start, last end] interval
+        from itertools import groupby
+        kept = [i for i, st in enumerate(ph_idx_seq) if ph_seq[st] != "SP"]
+        ph_seq_pred = np.array([ph_seq[ph_idx_seq[i]] for i in kept])
+        ph_intervals_pred = (ph_intervals[kept] if kept else np.array([])).clip(min=0, max=None)
+        runs = [(w, list(g)) for w, g in groupby(kept, key=lambda i: ph_idx_to_word_idx[ph_idx_seq[i]])]
+        word_seq_pred = np.array([word_seq[w] for w, _ in runs])
+        word_intervals_pred = np.array([[ph_intervals[g[0], 0], ph_intervals[g[-1], 1]]
+                                        for _, g in runs]).clip(min=0, max=None)
 
         self.ph_pred_seq = ph_seq_pred
         self.ph_intervals_pred = ph_intervals_pred
