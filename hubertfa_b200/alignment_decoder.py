@@ -129,7 +129,7 @@ class AlignmentDecoder:
     # How decode() / decode_batch() reach hfa_align_batch.  False (default): the C ABI is called directly
     # through ctypes.  True: through the ``hfa::align_batch`` torch custom op (same entry point, same stream).
     # Measured on B200, one T=500 / S=40 utterance per call (tools/time_decode.py): 0.40 ms per decode() through
-    # the op against 0.26 ms direct -- torch's Python custom-op dispatcher costs ~0.1 ms per call, more than the
+    # the op against 0.28 ms direct -- torch's Python custom-op dispatcher costs ~0.1 ms per call, more than the
     # 0.064 ms the kernels take, and predict_step (forced_alignment.py:174-176) pays it once per utterance.
     # The ops stay the interface for graph capture, the benchmark and the stage-level tests.
     dispatch_through_torch_op = False

@@ -155,3 +155,28 @@ def test_pipeline_result_survives_the_next_batch():
         for b, r in enumerate(want):
             idx, tim, _ = al.segments(out, b)
             assert np.array_equal(idx, r["ph_idx_seq"]) and np.array_equal(tim, r["ph_time_int"]), b
+
+
+def test_decode_direct_and_custom_op_dispatch_agree():
+    """decode() reaches hfa_align_batch through ctypes by default (latency) or through the hfa::align_batch
+    torch custom op (AlignmentDecoder.dispatch_through_torch_op): same entry point, same results, bit for bit."""
+    V = 63
+    T, S, vocab, items = _batch(6, 404, V, min_s=1, max_s=6, s_lo=3, s_hi=90)
+    outs = []
+    for through_op in (False, True):
+        dec = AlignmentDecoder(vocab, synth.MELSPEC_50FPS)
+        dec.dispatch_through_torch_op = through_op
+        runs = []
+        for it in items:
+            r = dec.decode(it["frame"].cuda(), it["edge"].cuda(), it["ctc"].cuda(), None, it["ph_seq"], it["word_seq"],
+                           it["ph_idx_to_word_idx"])
+            runs.append((r, dec.ph_idx_seq.copy(), dec.ph_time_int_pred.copy(), dec.frame_confidence.copy()))
+        res = dec.decode_batch([it["frame"].cuda() for it in items], [it["edge"].cuda() for it in items],
+                               [it["ph_seq"] for it in items])
+        outs.append((runs, res))
+    for (ra, ia, ta, fa), (rb, ib, tb, fb) in zip(outs[0][0], outs[1][0]):
+        assert list(ra[0]) == list(rb[0]) and list(ra[2]) == list(rb[2])
+        assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[3], rb[3]) and bits(ra[4]) == bits(rb[4])
+        assert np.array_equal(ia, ib) and np.array_equal(ta, tb) and np.array_equal(bits(fa), bits(fb))
+    assert np.array_equal(outs[0][1].ph_idx_seq, outs[1][1].ph_idx_seq)
+    assert np.array_equal(outs[0][1].raw_intervals, outs[1][1].raw_intervals)
