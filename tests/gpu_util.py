@@ -19,8 +19,13 @@ def run_core_gpu(ids_list, prob_logs, els, nes, ps=None, frame_length=0.02, voca
     T = [p.shape[0] for p in prob_logs]
     S = [len(i) for i in ids_list]
     plan = ops.AlignPlan(T, S, np.concatenate(ids_list), vocab, frame_length)
-    ws = plan.new_workspace(dev)
-    res = plan.new_result(dev)
+    # compute-sanitizer is closed on this pool: the workspace and the result blob sit between guard zones
+    # filled with a pattern, checked after the kernels have run (an out-of-bounds write of any kernel in any
+    # routing fails the test)
+    G = 1 << 16
+    ws_all = torch.full((G + max(plan.workspace_bytes, 256) + G,), 0xA5, dtype=torch.uint8, device=dev)
+    res_all = torch.full((G + plan.result_bytes + G,), 0x5A, dtype=torch.uint8, device=dev)
+    ws, res = ws_all[G:G + max(plan.workspace_bytes, 256)], res_all[G:G + plan.result_bytes]
     plan.upload(ws)
     cat = lambda xs, dt: torch.from_numpy(np.concatenate([np.asarray(x, dtype=dt).reshape(-1) for x in xs])).to(dev)
     pl, el, ne = cat(prob_logs, np.float32), cat(els, np.float32), cat(nes, np.float32)
@@ -46,6 +51,8 @@ def run_core_gpu(ids_list, prob_logs, els, nes, ps=None, frame_length=0.02, voca
     dpp = torch.empty(max(plan.total_frames, 1), dtype=torch.float32, device=dev)
     ops.backtrace(ws, plan.handle, res, fc, dpp)
     torch.cuda.synchronize()
+    for buf, pat, what in ((ws_all, 0xA5, "workspace"), (res_all, 0x5A, "result blob")):
+        assert bool((buf[:G] == pat).all()) and bool((buf[-G:] == pat).all()), f"a kernel wrote outside the {what}"
     v = plan.views(res.cpu().numpy())
     fc, dpp = fc.cpu().numpy(), dpp.cpu().numpy()
     dump_h = dp_dump.cpu().numpy() if dump else None
