@@ -22,7 +22,7 @@
 
 cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
                                float *dp_dump);
-cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
+cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, int max_pair_k, const int32_t *order, int n,
                                    float *dp_dump);
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
                               float *dp_dump);
@@ -150,6 +150,7 @@ struct hfa_plan {
     int32_t class_count[HFA_NUM_CLASSES + 1] = {0};
     int32_t cta_max_sp = 0, max_sp = 4;
     int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
+    int32_t warp_max_pair_k = 0, pair_count = 0;                     // ... of which in the SP-aware pair layout
     int32_t lat_begin = 0, lat_count = 0, lat_max_sp = 0;            // small-batch latency routing
     // banded (halo) kernel work lists: [0] S <= 256 utterances of a small batch (latency regime,
     // 2 states per lane), [1] long phoneme sequences (S > 256, band_k[1] states per lane)
@@ -519,12 +520,53 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         }
         // merged warp-kernel list: longest expected run time first (frames x per-frame cost, which
         // grows with the states per lane)
+        // SP-aware pair layout (hfa_dp_pair_body): the state axis regrouped into {SP, phoneme} pairs, KP pairs per
+        // lane.  Possible when no two SPs are adjacent and KP <= 4.  Decided for the BATCH, not per utterance: the
+        // merged kernel keeps one code path hot per class present, and a launch that mixes pair and plain bodies
+        // runs out of instruction cache (B200, config 4, DP stage: 0.462 ms all plain, 0.433 ms pairs only where
+        // they are cheaper (5 + 3 bodies hot, no_instruction the top stall), 0.370 ms every utterance in pairs).
+        // So: if the frames-weighted instruction count of the possible utterances is lower in pairs, all of them
+        // go there.  Instructions per frame counted in the SASS (loop bodies + the per-tile work / 8):
+        // 16 + 21 K plain, 17 + 25 KP in pairs.   HFA_PAIR = 0: never | 2: whenever possible | unset: as above.
+        // Only in the merged launch (the per-class launch modes keep the plain bodies).
+        int pair_mode = 1;
+        if (const char *e = std::getenv("HFA_PAIR")) pair_mode = std::atoi(e);
+        if (std::getenv("HFA_DP_MODE")) pair_mode = 0;
         std::vector<int32_t> warp_all;
+        std::vector<std::pair<int32_t, int>> pairable;          // (utterance, pairs per lane)
+        int64_t sum_pair = 0, sum_plain = 0;
         for (int c = 0; c < HFA_NUM_CLASSES; ++c) {
             warp_all.insert(warp_all.end(), lists[c].begin(), lists[c].end());
-            if (!lists[c].empty()) p->warp_max_k = c + 1;
+            for (int32_t b : lists[c]) {
+                const HfaUtt &m = p->utt[b];
+                const int32_t *id = ph_ids + m.seg_off;
+                int phon = 0;
+                bool ok = pair_mode > 0;
+                for (int32_t i = 0; i < m.S && ok; ++i) {
+                    phon += id[i] != 0;
+                    if (i > 0 && id[i] == 0 && id[i - 1] == 0) ok = false;
+                }
+                const int kp = (phon + (id[m.S - 1] == 0) + 31) / 32;
+                if (ok && kp <= HFA_PAIR_MAX_K) {
+                    pairable.push_back({b, kp});
+                    sum_pair += (int64_t)m.T * (17 + 25 * kp);
+                    sum_plain += (int64_t)m.T * (16 + 21 * (c + 1));
+                }
+                p->warp_max_k = std::max(p->warp_max_k, c + 1);
+            }
         }
-        auto cost = [&](int32_t b) { return (int64_t)p->utt[b].T * (2 + (p->utt[b].Sp + 31) / 32); };
+        if (pair_mode >= 2 || sum_pair < sum_plain)
+            for (const auto &bk : pairable) {
+                p->utt[bk.first].pair_k = bk.second;
+                p->warp_max_pair_k = std::max(p->warp_max_pair_k, bk.second);
+                p->pair_count += 1;
+            }
+        const bool old_order = std::getenv("HFA_WARP_ORDER") != nullptr;     // experiment: round 1's weights
+        auto cost = [&](int32_t b) {
+            const HfaUtt &m = p->utt[b];
+            if (old_order) return (int64_t)m.T * (2 + (m.Sp + 31) / 32);
+            return (int64_t)m.T * (m.pair_k > 0 ? 17 + 25 * m.pair_k : 16 + 21 * ((m.Sp + 31) / 32));
+        };
         std::sort(warp_all.begin(), warp_all.end(),
                   [&](int32_t a, int32_t b) { return cost(a) != cost(b) ? cost(a) > cost(b) : a < b; });
         p->warp_all_begin = (int32_t)p->order.size();
@@ -665,6 +707,8 @@ int hfa_plan_routing(const hfa_plan *p, int32_t out[8])
     out[7] = std::max(p->band_skew[0], p->band_skew[1]);
     return HFA_OK;
 }
+
+int32_t hfa_plan_pair_utterances(const hfa_plan *p) { return p ? p->pair_count : 0; }
 
 int64_t hfa_plan_debug_region(const hfa_plan *p, int32_t which, int64_t *n_bytes)
 {
@@ -904,7 +948,7 @@ static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_du
             if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: fork wait");
         }
         if (items[it].k == 0)
-            e = hfa_launch_dp_warp_any(c, p->warp_max_k, items[it].order, items[it].n, dp_dump);
+            e = hfa_launch_dp_warp_any(c, p->warp_max_k, p->warp_max_pair_k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k > 0)
             e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k == -3 || items[it].k == -4) {

@@ -19,6 +19,7 @@
 #define HFA_WARP_MAX_K 8         // states per lane in the warp-per-utterance kernel
 #define HFA_WARP_MAX_S (32 * HFA_WARP_MAX_K)
 #define HFA_CTA_K 8              // states per thread in the CTA-per-utterance kernel
+#define HFA_PAIR_MAX_K 4         // pairs per lane in the warp kernel's SP-aware pair layout (hfa_dp_pair_body)
 #define HFA_NUM_CLASSES 8        // K = 1..8 for the warp kernel (index K-1); class 8 -> CTA kernel
 
 struct HfaUtt {                  // 96 bytes, one per utterance, device copy lives in the workspace
@@ -35,7 +36,9 @@ struct HfaUtt {                  // 96 bytes, one per utterance, device copy liv
     int32_t tmap;                // index of the utterance's emission tensor map (banded / skewed routing), else -1
     int32_t skew_d;              // > 0: the skewed-wavefront kernel ran this utterance with this many frames of
                                  // skew per state; its kept dp uses the skewed layout (hfa_skew_dp_index)
-    int32_t pad_[3];
+    int32_t pair_k;              // > 0: the warp kernel runs this utterance in the SP-aware pair layout with this
+                                 // many {SP, phoneme} pairs per lane (hfa_dp_pair_body); 0: K states per lane
+    int32_t pad_[2];
 };
 static_assert(sizeof(HfaUtt) == 96, "HfaUtt is 96 bytes (16-byte multiple)");
 
@@ -171,6 +174,20 @@ __device__ __forceinline__ void hfa_tensor_load_2d(void *dst_smem, const void *t
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(hfa_smem_u32(dst_smem)), "l"(tmap), "r"(x), "r"(y), "r"(hfa_smem_u32(bar))
         : "memory");
+}
+// one lane of a CONVERGED warp (ptxas then emits TMA / bulk instructions once, from uniform registers, instead of
+// an ELECT / R2UR / BRA.U.ANY loop of ~20 instructions per copy)
+__device__ __forceinline__ bool hfa_elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ bool hfa_mbar_try_wait(uint64_t *bar, uint32_t parity)
 {

@@ -22,6 +22,7 @@
 // logs) = the 4.25 B/cell "algorithmic bytes" of DESIGN.md.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "hfa_common.cuh"
 
@@ -240,15 +241,20 @@ __device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&
 // warp per utterance
 // ---------------------------------------------------------------------------------------------
 constexpr int HFA_WARP_TILE = 8;      // frames per TMA stage (two stages = one backpointer word)
-constexpr int HFA_WARP_STAGES = 3;    // the copy of tile i+3 is issued when tile i has been consumed
+#ifndef HFA_WARP_NSTAGES
+#define HFA_WARP_NSTAGES 3
+#endif
+constexpr int HFA_WARP_STAGES = HFA_WARP_NSTAGES;    // the copy of tile i+3 is issued when tile i has been consumed
 
 template <int K> constexpr size_t hfa_warp_smem_bytes()
 {
     constexpr int nst = HFA_WARP_STAGES;
     // [stages x 8 rows x 32K floats][one slack row: the prefetch of "row 8" of the last stage]
     // [stages x 8 edge pairs][one slack pair][stages mbarriers]
+    // ... [pair tables of hfa_dp_pair_body, which shares this layout]
     return (size_t)(nst * HFA_WARP_TILE + 1) * 32 * K * sizeof(float) +
-           (size_t)(nst * HFA_WARP_TILE + 1) * sizeof(float2) + nst * sizeof(uint64_t);
+           (size_t)(nst * HFA_WARP_TILE + 1) * sizeof(float2) + nst * sizeof(uint64_t) +
+           (size_t)2 * 32 * HFA_PAIR_MAX_K * sizeof(int16_t);
 }
 
 template <int K, bool DUMP>
@@ -396,6 +402,271 @@ __device__ __forceinline__ void hfa_dp_warp_body(const HfaWs &ws, const int u,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// warp per utterance, SP-aware PAIR layout (big batches; SURVEY 7: "skip the f64 op when the source
+// state is SP")
+// ---------------------------------------------------------------------------------------------
+// An id-0 (SP) state never keeps a running maximum: curr is zeroed after every update (:226-228), so
+// for every frame t >= 2 its advance score is f32(f64(a) + 0.0 * ratio) = a (+0.0 for a = -0.0) -- no
+// conversion, no f64 op.  It also has only two candidates (stay / +1: the two-state jump needs an SP at
+// i-1, and in a sequence without adjacent SPs that is a phoneme).  To make that saving warp-uniform the
+// state axis is regrouped into PAIRS {B = the SP in front of phoneme n (if there is one), A = phoneme n};
+// a trailing SP is the B of one more pair without an A.  Every lane owns KP consecutive pairs:
+//     B[n]  = max(stayB, advA[n-1])                                  bit: +1
+//     A[n]  = max(stayA, advB[n], advA[n-1])   strict '>' in this order.  With a B the two candidates are
+//             "+1" and "+2 over the SP"; without one advB is -inf and advA[n-1] is the "+1" -- the bits
+//             are sorted out when a backpointer word is stored, once per 16 frames.
+// ~27 instructions per pair instead of ~21 per state, one lane exchange per frame instead of two, a third of
+// the conversions, and a dictionary-style sequence has ~1.67 states per pair.  Nothing else changes: the
+// emission tile is the same contiguous bulk copy into the same shared-memory ring as in hfa_dp_warp_body,
+// every slot reads its column through its own address register plus the frame's (uniform) row offset, and
+// the backpointer words keep their state order.  A pair without an SP reads its phoneme's column for B and
+// caps B's only candidate at -inf, so that B stays at -inf; a slot without a phoneme (the trailing pair,
+// the lanes past the last pair) computes garbage that only flows to the right, where nothing exists.
+// Frame 0 (:250-254) and frame 1 (the one frame where the curr of a leading SP is not 0, quirk q1) go
+// through the guarded body.
+// Eligibility (hfa_plan_create): no two adjacent SPs, pairs <= 32 * HFA_PAIR_MAX_K, cheaper than the
+// K-states-per-lane body.
+#ifndef HFA_PAIR_UNROLL
+#define HFA_PAIR_UNROLL 8        // measured on config 4 (B200, every utterance in pairs): DP stage 0.382 / 0.390 / 0.370 ms
+#endif                           // with 2 / 4 / 8 frames per chunk
+
+template <int KP, bool DUMP>
+__device__ __forceinline__ void hfa_dp_pair_body(const HfaWs &ws, const int u, float *__restrict__ dp_dump,
+                                                 unsigned char *smem_raw)
+{
+    constexpr int TT = HFA_WARP_TILE, NST = HFA_WARP_STAGES;
+    constexpr int UNR = HFA_PAIR_UNROLL;                      // frames per unrolled chunk (2, 4 or 8)
+    const int lane = threadIdx.x & 31;
+    const HfaUtt m = ws.utt[u];
+    const int T = m.T, S = m.S, Sp = m.Sp;
+    // the shared-memory layout of hfa_dp_warp_body<K> for this utterance's class, K = ceil(Sp / 32): rows of Sp
+    // floats, NST tiles of TT rows and one slack row; then the pair tables
+    const int row_max = (Sp + 31) & ~31;
+    float *tile0 = reinterpret_cast<float *>(smem_raw);
+    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + (NST * TT + 1) * row_max);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(edge0 + NST * TT + 1);
+    int16_t *tabA = reinterpret_cast<int16_t *>(bar + NST);     // state of every pair's phoneme / SP, or -1
+    int16_t *tabB = tabA + 32 * KP;
+
+    const int n_tiles = (T + TT - 1) / TT;
+    const float *g_emis = ws.emis + m.emis_off;
+    const float2 *g_edge = ws.edge2 + m.edge_off;
+    uint32_t *g_bp = ws.bp + m.bp_off;
+    const int32_t *ids = ws.ids + m.seg_off;
+    const double ratio = __ddiv_rn((double)T, (double)S);     // T / S (:186)
+    const uint32_t row_bytes = (uint32_t)Sp * 4u;
+    const uint32_t tile_bytes = TT * row_bytes;
+
+    auto issue = [&](int i) {                                  // one elected lane
+        const int st = i % NST;
+        const int t0 = i * TT;
+        const int rows = min(TT, T - t0);
+        const uint32_t bytes = (uint32_t)rows * row_bytes;
+        hfa_mbar_expect_tx(&bar[st], bytes + TT * (uint32_t)sizeof(float2));
+        hfa_bulk_load(tile0 + st * TT * Sp, g_emis + (int64_t)t0 * Sp, bytes, &bar[st]);
+        hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) hfa_mbar_init(&bar[s], 1);
+        hfa_fence_mbar_init();
+    }
+    for (int q = lane; q < 32 * KP; q += 32) {
+        tabA[q] = -1;
+        tabB[q] = -1;
+    }
+    __syncwarp();
+    if (hfa_elect_one())
+        for (int i = 0; i < NST && i < n_tiles; ++i) issue(i);
+    {
+        int before = 0;                                        // phonemes in front of this chunk of 32 states
+        for (int c0 = 0; c0 < S; c0 += 32) {
+            const int i = c0 + lane;
+            const bool is_ph = i < S && ids[i] != 0;
+            const uint32_t mask = __ballot_sync(0xffffffffu, is_ph);
+            const int pr = before + __popc(mask & ((1u << lane) - 1u));
+            if (i < S) (is_ph ? tabA : tabB)[pr] = (int16_t)i;
+            before += __popc(mask);
+        }
+    }
+    const bool sp0 = ids[0] == 0;
+    __syncwarp();
+
+    float dpA[KP], cuA[KP], dpB[KP], capB[KP];
+    uint32_t X[KP], Y[KP], Z[KP];                              // A: won by advB / by advA[n-1];  B: advanced
+    uint32_t aA[KP], aB[KP];                                   // shared address of the slot's column in ring row 0
+    const uint32_t tile_sa = hfa_smem_u32(tile0);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        dpA[k] = HFA_NEG_INF; cuA[k] = HFA_NEG_INF; dpB[k] = HFA_NEG_INF;
+        X[k] = 0; Y[k] = 0; Z[k] = 0;
+        const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
+        // a slot that does not exist reads its partner's column (any valid address): B is then capped below,
+        // A is garbage that nothing real ever reads
+        aA[k] = tile_sa + 4u * (uint32_t)(sa >= 0 ? sa : max(sb, 0));
+        aB[k] = tile_sa + 4u * (uint32_t)(sb >= 0 ? sb : max(sa, 0));
+        capB[k] = sb >= 0 ? __uint_as_float(0x7f800000u) : HFA_NEG_INF;
+    }
+    float cuB0 = 0.f;                                          // curr of a leading SP during frame 1 (q1)
+    const uint32_t edge_sa = hfa_smem_u32(edge0);
+
+    auto load = [&](uint32_t off, uint32_t eoff, float (&eA)[KP], float (&eB)[KP], float2 &ed) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(eA[k]) : "r"(aA[k] + off));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(eB[k]) : "r"(aB[k] + off));
+        }
+        ed = hfa_lds_f2(edge_sa + eoff);
+    };
+    // one frame t >= 1.  GUARD: frame 1 -- the leading SP still carries curr = e[0][0]
+    auto step = [&](auto guard, const int t, const uint32_t mbit, const float (&eA)[KP], const float (&eB)[KP],
+                    const float2 ed) {
+        float stayA[KP], stayB[KP], advA[KP], advB[KP];
+        const float xc = __fadd_rn(ed.x, 0.0f);               // -0.0 -> +0.0: f32(f64(a) + 0.0) without the f64
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            const int k = KP - 1 - kk;                         // the last pair's score crosses lanes: first
+            const float baseA = __fadd_rn(dpA[k], eA[k]);
+            advA[k] = hfa_advance(__fadd_rn(baseA, ed.x), cuA[k], ratio);
+            stayA[k] = __fadd_rn(baseA, ed.y);
+            const float baseB = __fadd_rn(dpB[k], eB[k]);
+            advB[k] = __fadd_rn(baseB, xc);
+            stayB[k] = __fadd_rn(baseB, ed.y);
+            if constexpr (decltype(guard)::value) {
+                if (k == 0 && t == 1 && lane == 0 && sp0) advB[0] = hfa_advance(__fadd_rn(baseB, ed.x), cuB0, ratio);
+            }
+        }
+        float up = __shfl_up_sync(0xffffffffu, advA[KP - 1], 1);
+        if (lane == 0) up = HFA_NEG_INF;                       // no phoneme in front of pair 0
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const float p3 = (k == 0) ? up : advA[k - 1];
+            const float p3b = fminf(p3, capB[k]);              // a B that does not exist stays at -inf
+            // alignment_decoder.py:210-228 on the pair: strict '>' scanned in the reference's order; curr of the
+            // phoneme = moved ? e : max(curr, e); the SP has no curr.
+            // Three predicates per pair (a fourth one for "moved" made ptxas spill predicates from two pairs per
+            // lane on; masks instead of predicates -- set.gt.u32 -- cost an FSETP + SEL each).
+            asm("{\n\t"
+                ".reg .pred qb, q1, q2;\n\t"
+                ".reg .f32 m, h;\n\t"
+                "setp.gt.f32 qb, %12, %7;\n\t"
+                "selp.f32 %0, %12, %7, qb;\n\t"
+                "@qb or.b32 %3, %3, %11;\n\t"
+                "setp.gt.f32 q1, %8, %9;\n\t"
+                "selp.f32 m, %8, %9, q1;\n\t"
+                "setp.gt.f32 q2, %6, m;\n\t"
+                "selp.f32 %1, %6, m, q2;\n\t"
+                "@q1 or.b32 %4, %4, %11;\n\t"
+                "@q2 or.b32 %5, %5, %11;\n\t"
+                "max.f32 h, %2, %10;\n\t"
+                "selp.f32 h, %10, h, q1;\n\t"
+                "selp.f32 %2, %10, h, q2;\n\t"
+                "}"
+                : "=&f"(dpB[k]), "=&f"(dpA[k]), "+f"(cuA[k]), "+r"(Z[k]), "+r"(X[k]), "+r"(Y[k])
+                : "f"(p3), "f"(stayB[k]), "f"(advB[k]), "f"(stayA[k]), "f"(eA[k]), "r"(mbit), "f"(p3b));
+        }
+        if constexpr (DUMP) {
+            const int64_t o = m.cell_off + (int64_t)t * S;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
+                if (sa >= 0) dp_dump[o + sa] = dpA[k];
+                if (sb >= 0) dp_dump[o + sb] = dpB[k];
+            }
+        }
+    };
+    // frame 0 (:250-254): state 0 is seeded, and state 1 too behind a leading SP
+    auto seed = [&](const float (&eA)[KP], const float (&eB)[KP]) {
+        if (lane == 0) {
+            if (sp0) {
+                dpB[0] = eB[0];
+                cuB0 = eB[0];
+            }
+            if (!sp0 || S > 1) {
+                dpA[0] = eA[0];
+                cuA[0] = eA[0];
+            }
+        }
+        if constexpr (DUMP) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
+                if (sa >= 0) dp_dump[m.cell_off + sa] = dpA[k];
+                if (sb >= 0) dp_dump[m.cell_off + sb] = dpB[k];
+            }
+        }
+    };
+
+    int st = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        hfa_mbar_wait(&bar[st], phase);
+        const uint32_t tl = (uint32_t)st * tile_bytes;        // row 0 of this stage (uniform)
+        const uint32_t et = (uint32_t)st * (TT * 8u);
+        const int rows = min(TT, T - i * TT);
+        const uint32_t mb0 = 1u << ((i & 1) * TT);             // backpointer bit of this tile's frame 0
+        float ea[KP], eb[KP], fa[KP], fb[KP];
+        float2 da, db;
+        load(tl, et, ea, eb, da);
+        if (rows == TT && i > 0) {
+            // full tile: two operand sets ping-pong, the next frame's operands are fetched before this
+            // frame's dependent chain (row 8 = the next stage's row 0 or the slack row: discarded).  Unrolled
+            // in chunks of UNR frames.  The merged kernel keeps one body hot per class present and the
+            // instruction cache is 32 KB: with pair AND plain bodies in one launch no_instruction was the top
+            // stall on config 4, which is why the plan moves a whole batch to pairs or none of it
+            uint32_t ro = tl, ec = et, mb = mb0;
+#pragma unroll 1
+            for (int c = 0; c < TT / UNR; ++c) {
+#pragma unroll
+                for (int tt = 0; tt < UNR; tt += 2) {
+                    load(ro + (uint32_t)(tt + 1) * row_bytes, ec + (uint32_t)(tt + 1) * 8u, fa, fb, db);
+                    step(std::false_type{}, i * TT + c * UNR + tt, mb << tt, ea, eb, da);
+                    load(ro + (uint32_t)(tt + 2) * row_bytes, ec + (uint32_t)(tt + 2) * 8u, ea, eb, da);
+                    step(std::false_type{}, i * TT + c * UNR + tt + 1, mb << (tt + 1), fa, fb, db);
+                }
+                ro += UNR * row_bytes;
+                ec += UNR * 8u;
+                mb <<= UNR;
+            }
+        } else {
+            for (int tt = 0; tt < rows; ++tt) {                // first tile / last, partial tile
+                if (tt > 0) load(tl + (uint32_t)tt * row_bytes, et + (uint32_t)tt * 8u, ea, eb, da);
+                if (i == 0 && tt == 0) seed(ea, eb);
+                else step(std::true_type{}, i * TT + tt, mb0 << tt, ea, eb, da);
+            }
+        }
+        if ((i & 1) || i == n_tiles - 1) {                     // 16 frames done (or the end): flush
+            uint32_t *row = g_bp + (int64_t)(i >> 1) * Sp;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
+                // with an SP in front: X = "+1", Y = "+2"; without: Y = "+1" (X is empty)
+                if (sa >= 0) row[sa] = sb >= 0 ? (X[k] | (Y[k] << 16)) : Y[k];
+                if (sb >= 0) row[sb] = Z[k];
+                X[k] = 0; Y[k] = 0; Z[k] = 0;
+            }
+        }
+        __syncwarp();                                          // every lane is done reading stage `st`
+        if (i + NST < n_tiles) {
+            if (hfa_elect_one()) issue(i + NST);
+        }
+        if (++st == NST) {
+            st = 0;
+            phase ^= 1u;
+        }
+    }
+
+    // scores of the last two states at T-1 for the end-state rule (:269-272)
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
+        if (sa >= 0 && sa >= S - 2) ws.dp_last[2 * u + (S - 1 - sa)] = dpA[k];
+        if (sb >= 0 && sb >= S - 2) ws.dp_last[2 * u + (S - 1 - sb)] = dpB[k];
+    }
+}
+
 // one state class per launch (used when the classes are spread over streams)
 template <int K, bool DUMP>
 __global__ void __launch_bounds__(32)
@@ -420,6 +691,14 @@ hfa_dp_warp_any_kernel(HfaWs ws, const int32_t *__restrict__ order, int n,
     const int item = blockIdx.x;
     if (item >= n) return;
     const int u = order[item];
+    const int kp = ws.utt[u].pair_k;                    // > 0: the SP-aware pair layout was chosen for it
+    if (kp > 0) {
+        if (kp == 1) hfa_dp_pair_body<1, DUMP>(ws, u, dp_dump, smem_raw);
+        else if (kp == 2) hfa_dp_pair_body<2, DUMP>(ws, u, dp_dump, smem_raw);
+        else if (kp == 3) hfa_dp_pair_body<3, DUMP>(ws, u, dp_dump, smem_raw);
+        else hfa_dp_pair_body<4, DUMP>(ws, u, dp_dump, smem_raw);
+        return;
+    }
     const int k = (ws.utt[u].Sp + 31) >> 5;
     if (k <= 1) hfa_dp_warp_body<1, DUMP>(ws, u, dp_dump, smem_raw);
     else if (k == 2) hfa_dp_warp_body<2, DUMP>(ws, u, dp_dump, smem_raw);
@@ -1240,12 +1519,14 @@ static cudaError_t launch_any(const HfaLaunchCtx &c, size_t smem, const int32_t 
     return cudaGetLastError();
 }
 
-// all warp-kernel classes in one launch; max_k = largest states-per-lane class present
-cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, const int32_t *order, int n,
+// all warp-kernel classes in one launch; max_k = largest states-per-lane class present, ceil(Sp / 32) (the pair
+// layout uses the shared-memory layout of its utterance's class), max_pair_k = largest pairs-per-lane class
+cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, int max_pair_k, const int32_t *order, int n,
                                    float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    if (max_k < 1 || max_k > 8) return cudaErrorInvalidValue;
+    if (max_k < 1 || max_k > 8 || max_pair_k < 0 || max_pair_k > HFA_PAIR_MAX_K) return cudaErrorInvalidValue;
+
     static const size_t bytes[9] = {0, hfa_warp_smem_bytes<1>(), hfa_warp_smem_bytes<2>(),
                                     hfa_warp_smem_bytes<3>(), hfa_warp_smem_bytes<4>(),
                                     hfa_warp_smem_bytes<5>(), hfa_warp_smem_bytes<6>(),

@@ -71,7 +71,8 @@ class AlignPlan:
         out = (C.c_int32 * 8)()
         check(self._lib.hfa_plan_routing(self._h, C.byref(out)))
         return dict(warp_utts=out[0], band_warps=out[1], band_k=out[2], big_band_warps=out[3],
-                    big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]), skew_d=out[7])
+                    big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]), skew_d=out[7],
+                    pair_utts=int(self._lib.hfa_plan_pair_utterances(self._h)))
 
     def algorithmic_bytes_fused(self, dtype: int = _lib.DTYPE_F32) -> int:
         return int(self._lib.hfa_plan_algorithmic_bytes_fused(self._h, dtype))

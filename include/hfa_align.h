@@ -106,6 +106,10 @@ int hfa_plan_algorithmic_bytes(const hfa_plan *plan, int32_t dtype, int64_t out[
  * forward pass keeps dp for the backtrace, out[7] > 0: those lists run in the skewed-wavefront kernel
  * (one state per lane, out[2] / out[4] == 1) with that many frames of skew per state. */
 int hfa_plan_routing(const hfa_plan *plan, int32_t out[8]);
+/* How many of the out[0] utterances run in the warp kernel's SP-aware pair layout (the state axis regrouped into
+ * {SP, phoneme} pairs so that the advance out of an SP needs no f64 arithmetic; tools/alignment_decoder.py:182-187
+ * with curr == 0 at :226-228).  Chosen per utterance at hfa_plan_create. */
+int32_t hfa_plan_pair_utterances(const hfa_plan *plan);
 
 /* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace, zeroes
  * the banded kernel's exchange table and writes the TMA tensor maps of its emission windows (they

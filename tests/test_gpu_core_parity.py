@@ -11,13 +11,14 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1", "2k4", "2k8", "2nk", "2rc", "2s2", "2s3", "2s2slow", "2s2nk", "auto"],
-                ids=["warp-per-utterance", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
+@pytest.fixture(params=["0", "0p2", "0p0", "1", "2k4", "2k8", "2nk", "2rc", "2s2", "2s3", "2s2slow", "2s2nk", "auto"],
+                ids=["warp-per-utterance", "warp-pair-layout-forced", "warp-plain-layout-only", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
                      "banded-no-dp-store", "banded-row-copies", "skew-d2", "skew-d3", "skew-d2-guarded-body",
                      "skew-d2-no-dp-store", "auto"])
 def routing(request, monkeypatch):
     """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
-    S > 256 in the CTA kernel; 1 = utterances with > 64 states go to the multi-warp CTA kernel;
+    S > 256 in the CTA kernel -- the SP-aware pair layout where the plan's cost rule picks it, wherever it is
+    possible (HFA_PAIR=2) or nowhere (HFA_PAIR=0); 1 = utterances with > 64 states go to the multi-warp CTA kernel;
     2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane, the backtrace
     reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path, or (row-copies)
     without the TMA tensor maps; skew-* = everything (S > 256 included) in the skewed-wavefront kernel
@@ -27,6 +28,8 @@ def routing(request, monkeypatch):
         monkeypatch.setenv("HFA_LATENCY_MODE", request.param[0])
         monkeypatch.setenv("HFA_BIG_KERNEL", "band" if request.param[0] == "2" else "cta")
         monkeypatch.setenv("HFA_LAT_KERNEL", "skew" if request.param.startswith("2s") else "band")
+    if request.param in ("0p2", "0p0"):
+        monkeypatch.setenv("HFA_PAIR", request.param[2])
     if request.param in ("2k4", "2k8"):
         monkeypatch.setenv("HFA_BIG_K", request.param[2])
     if request.param.startswith("2s"):
@@ -108,6 +111,73 @@ def test_ties_go_to_the_earlier_candidate(routing):
     out = run_core_gpu([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], [c[3] for c in cases])
     for c, g in zip(cases, out):
         check_core_against_oracle(c[0], c[1], c[2], c[3], g)
+
+
+def _pairable_ids(rng, S, lead, trail, max_word):
+    """Random sequence without adjacent SPs: [SP] word SP word ... [SP], words of 1..max_word phonemes."""
+    ids = [0] if lead else []
+    while len(ids) < S:
+        ids += [int(x) for x in rng.integers(1, 30, int(rng.integers(1, max_word + 1)))]
+        ids.append(0)
+    ids = ids[:S]
+    if trail:
+        if S >= 2 and ids[-2] == 0:
+            ids[-2] = 7
+        ids[-1] = 0
+    elif ids[-1] == 0 and (S == 1 or ids[-2] != 0):
+        ids[-1] = 9 if not (S == 1 and lead) else 0
+    return np.array(ids, dtype=np.int32)
+
+
+@pytest.mark.parametrize("pair", ["2", "0"], ids=["pair-layout", "plain-layout"])
+def test_sp_pair_layout_edge_cases(pair, monkeypatch):
+    """The SP-aware pair layout of the warp kernel (hfa_dp_pair_body) on the shapes its regrouping has to get
+    right: with / without a leading SP (frame 1 is the one frame where an SP's curr is not 0, quirk q1), with /
+    without a trailing SP (a pair without a phoneme), words of 1..4 phonemes (pairs without an SP), 1..4 pairs per
+    lane, T = 1 / 2 / tile boundaries, coarse-grid values (ties), sprinkled -inf, and -0.0 everywhere (the SP
+    shortcut must still give f32(f64(a) + 0.0) = +0.0 for a = -0.0).  Every dp cell and backpointer vs the oracle."""
+    from hubertfa_b200 import ops
+    monkeypatch.setenv("HFA_LATENCY_MODE", "0")
+    monkeypatch.setenv("HFA_PAIR", pair)
+    rng = np.random.default_rng(424242)
+    ids_l, e_l, el_l, ne_l, p_l = [], [], [], [], []
+    shapes = [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2), (7, 3), (8, 5), (9, 4), (16, 8), (17, 30), (24, 33),
+              (25, 64), (40, 65), (33, 100), (64, 128), (70, 150), (50, 200), (41, 213), (90, 256), (300, 90)]
+    for i, (T, S) in enumerate(shapes * 3):
+        lead, trail, mw = bool(i & 1), bool(i & 2), 1 + i % 4
+        ids = _pairable_ids(rng, S, lead, trail, mw)
+        mode = i % 4
+        if mode == 0:
+            e = (-rng.exponential(3.0, (T, S))).astype(np.float32)
+            p = rng.random(T).astype(np.float32)
+        elif mode == 1:
+            e = (-rng.integers(0, 4, (T, S)) * 0.5).astype(np.float32)
+            p = (rng.integers(0, 3, T) * 0.5).astype(np.float32)
+        elif mode == 2:
+            e = np.full((T, S), -1.0, np.float32)
+            p = np.full(T, 0.25, np.float32)
+        else:
+            e = np.where(rng.random((T, S)) < 0.5, -0.0, 0.0).astype(np.float32)
+            p = rng.random(T).astype(np.float32)
+        if i % 5 == 0:
+            e[rng.random((T, S)) < 0.05] = -np.inf
+        _, ep = onp.edge_streams(p)
+        el, ne = onp.edge_logs(ep)
+        if mode == 3:                                  # -0.0 edge logs: only reachable at this boundary
+            el = np.where(rng.random(T) < 0.5, -0.0, 0.0).astype(np.float32)
+            ne = np.where(rng.random(T) < 0.5, -0.0, 0.0).astype(np.float32)
+        ids_l.append(ids); e_l.append(e); el_l.append(el); ne_l.append(ne); p_l.append(p)
+    plan = ops.AlignPlan([e.shape[0] for e in e_l], [len(i) for i in ids_l], np.concatenate(ids_l), 4096, 0.02)
+    r = plan.routing()
+    n_pairable = sum(1 for ids in ids_l if ((ids != 0).sum() + (ids[-1] == 0) + 31) // 32 <= 4)
+    assert r["warp_utts"] == len(ids_l) and r["pair_utts"] == (n_pairable if pair == "2" else 0)
+    assert n_pairable >= 40
+    out = run_core_gpu(ids_l, e_l, el_l, ne_l, p_l, 0.02)
+    for i, g in enumerate(out):
+        try:
+            check_core_against_oracle(ids_l[i], e_l[i], el_l[i], ne_l[i], g, p_l[i], 0.02)
+        except AssertionError as err:
+            raise AssertionError(f"utterance {i} (T={e_l[i].shape[0]}, S={len(ids_l[i])}, ids={ids_l[i][:12]}): {err}") from err
 
 
 def test_minus_inf_emissions_do_not_create_nan():

@@ -54,6 +54,30 @@ def test_plan_layout_and_statuses():
     assert empty.total_cells == 0 and empty.workspace_bytes >= 0
 
 
+def test_pair_layout_is_chosen_for_the_batch(monkeypatch):
+    """hfa_plan_create moves a batch to the warp kernel's SP-aware pair layout as a whole (every utterance without
+    adjacent SPs and with at most 4 pairs per lane) when that lowers the frames-weighted instruction count
+    (17 + 25 x pairs-per-lane against 16 + 21 x states-per-lane), else not at all."""
+    from hubertfa_b200 import ops
+    monkeypatch.setenv("HFA_LATENCY_MODE", "0")
+    alt = lambda S: np.array([0 if i % 2 == 0 else 5 for i in range(S)], np.int32)     # SP ph SP ph ...
+    dictionary = [alt(40), alt(30), alt(255),           # 20 / 15 / 128 pairs: 1 / 1 / 4 per lane vs 2 / 1 / 8 states
+                  np.array([0, 0] + [4] * 60, np.int32),    # adjacent SPs: never
+                  np.full(200, 3, np.int32)]                # 200 pairs, 7 per lane: never
+    nosp = [np.full(50, 3, np.int32), np.full(90, 7, np.int32), alt(30)]   # pairs = states: plain is cheaper
+    mk = lambda seqs: ops.AlignPlan([100] * len(seqs), [len(s) for s in seqs], np.concatenate(seqs), 63, 0.02)
+    r = mk(dictionary).routing()
+    assert r["warp_utts"] == 5 and r["pair_utts"] == 3
+    assert mk(nosp).routing()["pair_utts"] == 0
+    monkeypatch.setenv("HFA_PAIR", "2")
+    assert mk(nosp).routing()["pair_utts"] == 3
+    monkeypatch.setenv("HFA_PAIR", "0")
+    assert mk(dictionary).routing()["pair_utts"] == 0
+    monkeypatch.delenv("HFA_PAIR")
+    monkeypatch.setenv("HFA_DP_MODE", "serial")        # the per-class launch modes keep the plain bodies
+    assert mk(dictionary).routing()["pair_utts"] == 0
+
+
 def test_compute_entry_points_fail_loudly_without_cuda():
     import torch
     from hubertfa_b200 import ops
