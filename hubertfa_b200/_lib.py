@@ -47,6 +47,8 @@ SYMBOLS = {
     "hfa_plan_debug_region": (_i64, [_vp, _i32, C.POINTER(_i64)]),
     "hfa_plan_routing": (C.c_int, [_vp, C.POINTER(_i32 * 8)]),
     "hfa_plan_pair_utterances": (_i32, [_vp]),
+    "hfa_plan_stored_emission_bytes": (_i64, [_vp]),
+    "hfa_debug_unpack_emissions": (C.c_int, [_vp, _vp, _vp, _vp]),
     "hfa_plan_upload": (C.c_int, [_vp, _vp, _vp]),
     "hfa_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hfa_set_inputs_device": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -22,6 +22,7 @@
 
 cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
                                float *dp_dump);
+cudaError_t hfa_launch_unpack_emissions(const HfaLaunchCtx &c, int total_row_blocks, float *out);
 cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, int max_pair_k, const int32_t *order, int n,
                                    float *dp_dump);
 cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
@@ -142,6 +143,10 @@ struct hfa_plan {
     double frame_length = 0.0;
     std::vector<HfaUtt> utt;
     std::vector<int32_t> ids;
+    std::vector<int32_t> col_ids;              // compacted emission columns (HfaWs::col_ids / colmap)
+    std::vector<uint8_t> colmap;
+    int32_t n_compact = 0;
+    int64_t stored_emis = 0;                   // floats the emission kernels write (compacted where possible)
     std::vector<int64_t> frame_off, seg_off;   // [n+1]
     // bucket lists: class c = K-1 for the warp kernel (K states per lane), class 8 = CTA kernel,
     // then the backtrace list (valid utterances by descending T, then the invalid ones)
@@ -168,6 +173,7 @@ struct hfa_plan {
     int64_t total_frames = 0, total_states = 0, total_cells = 0, padded_cells = 0;
     int64_t total_words = 0, total_edge = 0;
     // byte offsets
+    int64_t o_colids = 0, o_colmap = 0, o_emode = 0;
     int64_t o_utt = 0, o_ids = 0, o_order = 0, o_rowblk = 0, o_blkutt = 0, o_inputs = 0, head_bytes = 0;
     int64_t o_emis = 0, o_edge2 = 0, o_edgep = 0, o_bp = 0, o_path = 0, o_revi = 0, o_revt = 0,
             o_last = 0, o_dpst = 0, o_jump = 0, o_moves = 0, o_rowent = 0, o_band_items = 0, o_jblk_utt = 0, o_jblk_first = 0, o_band_ticket = 0, o_band_xchg = 0, band_bytes = 0, o_tmaps = 0, ws_bytes = 0;
@@ -220,6 +226,9 @@ HfaWs make_ws(const hfa_plan *p, void *workspace)
     w.jblk_utt = reinterpret_cast<const int32_t *>(b + p->o_jblk_utt);
     w.jblk_first = reinterpret_cast<const int32_t *>(b + p->o_jblk_first);
     w.tmaps = (p->n_tmaps > 0 && tensor_map_encoder() != nullptr) ? b + p->o_tmaps : nullptr;
+    w.col_ids = reinterpret_cast<const int32_t *>(b + p->o_colids);
+    w.colmap = reinterpret_cast<const uint8_t *>(b + p->o_colmap);
+    w.emis_mode = reinterpret_cast<int32_t *>(b + p->o_emode);
     w.band_items = reinterpret_cast<const HfaBandItem *>(b + p->o_band_items);
     w.band_ticket = reinterpret_cast<int32_t *>(b + p->o_band_ticket);
     w.band_xchg = reinterpret_cast<uint4 *>(b + p->o_band_xchg);
@@ -555,12 +564,38 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 p->warp_max_k = std::max(p->warp_max_k, c + 1);
             }
         }
+        // Compacted emission rows for those utterances (HfaWs::colmap): every slot of the pair layout reads its
+        // column through its own address register, so pointing states with the same id at ONE column is free.
+        // HFA_COMPACT=0 keeps the plain [T][Sp] rows.
+        bool compact = vocab_size <= 255;
+        if (const char *e = std::getenv("HFA_COMPACT")) compact = compact && e[0] != '0';
+        p->col_ids.assign((size_t)(p->total_states + 4 * (int64_t)n_utt), vocab_size);
+        p->colmap.assign((size_t)p->total_states, 0);
         if (pair_mode >= 2 || sum_pair < sum_plain)
             for (const auto &bk : pairable) {
-                p->utt[bk.first].pair_k = bk.second;
+                HfaUtt &m = p->utt[bk.first];
+                m.pair_k = bk.second;
                 p->warp_max_pair_k = std::max(p->warp_max_pair_k, bk.second);
                 p->pair_count += 1;
+                if (!compact) continue;
+                const int32_t *id = ph_ids + m.seg_off;
+                int col_of[256];
+                std::fill(col_of, col_of + 256, -1);
+                for (int32_t i = 0; i < m.S; ++i) col_of[id[i]] = 0;
+                int d = 0;
+                for (int v = 0; v < vocab_size; ++v)
+                    if (col_of[v] == 0) col_of[v] = d++;
+                const int dp = (d + 3) & ~3;
+                if (dp >= m.Sp) continue;                              // nothing to gain
+                m.Dp = dp;
+                p->n_compact += 1;
+                int32_t *ci = p->col_ids.data() + m.seg_off + 4 * (int64_t)bk.first;
+                for (int v = 0; v < vocab_size; ++v)
+                    if (col_of[v] >= 0) ci[col_of[v]] = v;
+                for (int32_t i = 0; i < m.S; ++i) p->colmap[(size_t)(m.seg_off + i)] = (uint8_t)col_of[id[i]];
             }
+        for (const HfaUtt &m : p->utt)
+            if (m.status == 0) p->stored_emis += (int64_t)m.T * (m.Dp > 0 ? m.Dp : m.Sp);
         const bool old_order = std::getenv("HFA_WARP_ORDER") != nullptr;     // experiment: round 1's weights
         auto cost = [&](int32_t b) {
             const HfaUtt &m = p->utt[b];
@@ -594,6 +629,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_band_items = region((int64_t)p->band_items.size() * sizeof(HfaBandItem));
         p->o_jblk_utt = region((int64_t)p->jblk_utt.size() * 4);
         p->o_jblk_first = region((int64_t)p->jblk_first.size() * 4);
+        p->o_colids = region(p->n_compact > 0 ? (int64_t)p->col_ids.size() * 4 : 0);
+        p->o_colmap = region(p->n_compact > 0 ? (int64_t)p->colmap.size() : 0);
         p->head_bytes = o;
         p->o_inputs = region((int64_t)n_utt * sizeof(HfaInput));
         p->o_emis = region(emis * 4);
@@ -604,6 +641,7 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->o_revi = region(p->total_states * 4);
         p->o_revt = region(p->total_states * 4);
         p->o_last = region((int64_t)n_utt * 8);
+        p->o_emode = region(p->n_compact > 0 ? (int64_t)n_utt * 4 : 0);
         p->o_dpst = region(p->dp_store_elems * 4);
         const bool jump_tables = p->dp_store_elems > 0;      // latency plans: parallel backtrace
         p->o_jump = region(jump_tables ? words : 0);
@@ -629,6 +667,10 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         if (!p->jblk_utt.empty())
             std::memcpy(p->head.data() + p->o_jblk_utt, p->jblk_utt.data(), p->jblk_utt.size() * 4);
         std::memcpy(p->head.data() + p->o_jblk_first, p->jblk_first.data(), p->jblk_first.size() * 4);
+        if (p->n_compact > 0) {
+            std::memcpy(p->head.data() + p->o_colids, p->col_ids.data(), p->col_ids.size() * 4);
+            if (!p->colmap.empty()) std::memcpy(p->head.data() + p->o_colmap, p->colmap.data(), p->colmap.size());
+        }
         std::memcpy(p->head.data() + p->o_rowblk, p->row_blocks.data(), (size_t)(n_utt + 1) * 4);
         if (!p->block_utt.empty())
             std::memcpy(p->head.data() + p->o_blkutt, p->block_utt.data(), p->block_utt.size() * 4);
@@ -709,6 +751,7 @@ int hfa_plan_routing(const hfa_plan *p, int32_t out[8])
 }
 
 int32_t hfa_plan_pair_utterances(const hfa_plan *p) { return p ? p->pair_count : 0; }
+int64_t hfa_plan_stored_emission_bytes(const hfa_plan *p) { return p ? p->stored_emis * 4 : 0; }
 
 int64_t hfa_plan_debug_region(const hfa_plan *p, int32_t which, int64_t *n_bytes)
 {
@@ -755,6 +798,11 @@ int hfa_plan_upload(const hfa_plan *p, void *workspace, void *stream)
         if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload: tensor maps");
     } catch (const std::bad_alloc &) {
         return fail(HFA_ERR_NOMEM, "hfa_plan_upload: out of host memory");
+    }
+    if (p->n_compact > 0) {        // no emissions yet: plain rows
+        e = cudaMemsetAsync(static_cast<unsigned char *>(workspace) + p->o_emode, 0, (size_t)p->n_utt * 4,
+                            static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "hfa_plan_upload: emission mode reset");
     }
     if (p->band_bytes > 0) {       // band tickets + exchange slots start (and are left) all-zero
         e = cudaMemsetAsync(static_cast<unsigned char *>(workspace) + p->o_band_ticket, 0,
@@ -1102,6 +1150,16 @@ int hfa_debug_unpack_dp(const hfa_plan *p, const void *workspace, int32_t utt, f
     HfaLaunchCtx c = make_ctx(p, const_cast<void *>(workspace), stream);
     cudaError_t e = hfa_launch_unpack_dp(c, utt, out);
     if (e != cudaSuccess) return cuda_fail(e, "hfa_debug_unpack_dp: launch");
+    g_launches += 1;
+    return HFA_OK;
+}
+
+int hfa_debug_unpack_emissions(const hfa_plan *p, const void *workspace, float *out, void *stream)
+{
+    if (!p || !workspace || !out) return fail(HFA_ERR_ARG, "hfa_debug_unpack_emissions: NULL argument");
+    HfaLaunchCtx c = make_ctx(p, const_cast<void *>(workspace), stream);
+    cudaError_t e = hfa_launch_unpack_emissions(c, p->n_utt > 0 ? p->row_blocks[p->n_utt] : 0, out);
+    if (e != cudaSuccess) return cuda_fail(e, "hfa_debug_unpack_emissions: launch");
     g_launches += 1;
     return HFA_OK;
 }

@@ -203,6 +203,10 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     const float2 *edge2 = ws.edge2 + m.edge_off;
     const double ratio = __ddiv_rn((double)T, (double)S);
     const bool lead_sp = (ids[0] == 0) && (S > 1);
+    // emission rows: plain [T][Sp], or compacted to one column per distinct id (HfaWs::colmap)
+    const bool compact = m.Dp > 0 && ws.emis_mode[u] != 0;
+    const int Ep = compact ? m.Dp : Sp;
+    const uint8_t *cmap = ws.colmap + m.seg_off;
     float4 *stage = stage_sm[warp];
     float *dpath = dpath_sm[warp];
     float d = 0.0f, cu = 0.0f, carry_d = 0.0f;          // dp_path[-1] := 0 (:286)
@@ -218,10 +222,10 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
     struct Raw { float x, y; float2 ed; int id, st, sprev; };
     auto gather = [&](int round, int st, int sprev) {
         const int t = min(round * 32 + lane, T - 1);         // clamped: always a valid address
-        const float *row = emis + (int64_t)t * Sp;
+        const float *row = emis + (int64_t)t * Ep;
         Raw g;
-        g.x = row[st];
-        g.y = row[sprev];
+        g.x = row[compact ? (int)cmap[st] : st];
+        g.y = row[compact ? (int)cmap[sprev] : sprev];
         g.ed = edge2[t];
         g.id = ids[st];
         g.st = st;

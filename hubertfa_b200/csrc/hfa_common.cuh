@@ -38,7 +38,9 @@ struct HfaUtt {                  // 96 bytes, one per utterance, device copy liv
                                  // skew per state; its kept dp uses the skewed layout (hfa_skew_dp_index)
     int32_t pair_k;              // > 0: the warp kernel runs this utterance in the SP-aware pair layout with this
                                  // many {SP, phoneme} pairs per lane (hfa_dp_pair_body); 0: K states per lane
-    int32_t pad_[2];
+    int32_t Dp;                  // > 0: the emission kernels may store this utterance's rows COMPACTED to one column
+                                 // per distinct phoneme id (row stride Dp floats instead of Sp; see HfaWs::colmap)
+    int32_t pad_;
 };
 static_assert(sizeof(HfaUtt) == 96, "HfaUtt is 96 bytes (16-byte multiple)");
 
@@ -81,6 +83,14 @@ struct HfaWs {
     // 128-byte TMA tensor maps (CUtensorMap) over emis[t][s] of the banded utterances: box = 16 frames
     // x one band window; NULL when the driver entry point is unavailable (row copies are used then)
     const void *tmaps;
+    // Compacted emission rows (utterances with Dp > 0, i.e. the warp kernel's pair layout): states with the same
+    // phoneme id have the same emission (prob_log[t, ids[s]], alignment_decoder.py:239), and 40 % of a
+    // dictionary-style sequence is the one id 0 -- so hfa_emission stores one column per DISTINCT id,
+    // emis[t][colmap[s]], about half the bytes written and read back.  hfa_pack_emissions takes per-state values
+    // and stores the plain [T][Sp] rows; emis_mode[u] says which of the two the last writer left (1 = compacted).
+    const int32_t *col_ids;      // [seg_off + 4 u + c]: phoneme id of column c (ascending; pads = vocab -> -inf)
+    const uint8_t *colmap;       // [seg_off + s]: column of state s
+    int32_t *emis_mode;          // [n_utt]
     const HfaBandItem *band_items;   // banded kernel work list (see hfa_dp_band_kernel)
     int32_t *band_ticket;        // [2] work-item tickets of the two band lists (self-resetting)
     uint4 *band_xchg;            // {dp, tag, p.lo, tag}{p.hi, tag, 0, tag} of a band's last 32 states per tile;

@@ -242,7 +242,8 @@ __device__ __forceinline__ void hfa_frame_p(const float (&e)[K], const double (&
 // ---------------------------------------------------------------------------------------------
 constexpr int HFA_WARP_TILE = 8;      // frames per TMA stage (two stages = one backpointer word)
 #ifndef HFA_WARP_NSTAGES
-#define HFA_WARP_NSTAGES 3
+#define HFA_WARP_NSTAGES 2      // measured on config 4 (B200): 13 -> 20 resident warps per SM, DP stage 0.370 -> 0.362 ms (pairs),
+                                // 0.480 -> 0.457 ms (plain); the next tile still has a whole tile time (~1 us) to land
 #endif
 constexpr int HFA_WARP_STAGES = HFA_WARP_NSTAGES;    // the copy of tile i+3 is issued when tile i has been consumed
 
@@ -455,7 +456,12 @@ __device__ __forceinline__ void hfa_dp_pair_body(const HfaWs &ws, const int u, f
     uint32_t *g_bp = ws.bp + m.bp_off;
     const int32_t *ids = ws.ids + m.seg_off;
     const double ratio = __ddiv_rn((double)T, (double)S);     // T / S (:186)
-    const uint32_t row_bytes = (uint32_t)Sp * 4u;
+    // emission rows: plain [T][Sp], or compacted to one column per distinct id (HfaWs::colmap) -- then several
+    // slots simply hold the same column address
+    const bool compact = m.Dp > 0 && ws.emis_mode[u] != 0;
+    const int Ep = compact ? m.Dp : Sp;
+    const uint8_t *cmap = ws.colmap + m.seg_off;
+    const uint32_t row_bytes = (uint32_t)Ep * 4u;
     const uint32_t tile_bytes = TT * row_bytes;
 
     auto issue = [&](int i) {                                  // one elected lane
@@ -464,7 +470,7 @@ __device__ __forceinline__ void hfa_dp_pair_body(const HfaWs &ws, const int u, f
         const int rows = min(TT, T - t0);
         const uint32_t bytes = (uint32_t)rows * row_bytes;
         hfa_mbar_expect_tx(&bar[st], bytes + TT * (uint32_t)sizeof(float2));
-        hfa_bulk_load(tile0 + st * TT * Sp, g_emis + (int64_t)t0 * Sp, bytes, &bar[st]);
+        hfa_bulk_load(tile0 + st * TT * Ep, g_emis + (int64_t)t0 * Ep, bytes, &bar[st]);
         hfa_bulk_load(edge0 + st * TT, g_edge + t0, TT * (uint32_t)sizeof(float2), &bar[st]);
     };
 
@@ -505,8 +511,9 @@ __device__ __forceinline__ void hfa_dp_pair_body(const HfaWs &ws, const int u, f
         const int sa = tabA[lane * KP + k], sb = tabB[lane * KP + k];
         // a slot that does not exist reads its partner's column (any valid address): B is then capped below,
         // A is garbage that nothing real ever reads
-        aA[k] = tile_sa + 4u * (uint32_t)(sa >= 0 ? sa : max(sb, 0));
-        aB[k] = tile_sa + 4u * (uint32_t)(sb >= 0 ? sb : max(sa, 0));
+        const int ca = sa >= 0 ? sa : max(sb, 0), cb = sb >= 0 ? sb : max(sa, 0);
+        aA[k] = tile_sa + 4u * (uint32_t)(compact ? cmap[ca] : ca);
+        aB[k] = tile_sa + 4u * (uint32_t)(compact ? cmap[cb] : cb);
         capB[k] = sb >= 0 ? __uint_as_float(0x7f800000u) : HFA_NEG_INF;
     }
     float cuB0 = 0.f;                                          // curr of a leading SP during frame 1 (q1)

@@ -102,9 +102,11 @@ hfa_emission_block_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     const int u = ws.block_utt[blockIdx.x];
     const HfaUtt m = ws.utt[u];
     const HfaInput in = ws.inputs[u];
-    const int T = m.T, S = m.S, Sp = m.Sp;
+    const bool compact = m.Dp > 0;                                           // see the stream kernel
+    const int T = m.T, S = compact ? m.Dp : m.S, Sp = compact ? m.Dp : m.Sp;
     const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
     const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
+    if (compact && t_base == 0 && threadIdx.x == 0) ws.emis_mode[u] = 1;
 
     // A. logits block -> smem (rows past T re-read row T-1: valid memory, results never stored)
     {
@@ -132,11 +134,11 @@ hfa_emission_block_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     // B. ids, keep mask, kept list
     if (tid < 8) mask_sm[tid] = (tid == 0) ? 1u : 0u;                        // id 0 always kept (:39)
     __syncthreads();
-    const int32_t *ids = ws.ids + m.seg_off;
+    const int32_t *ids = compact ? ws.col_ids + m.seg_off + 4 * (int64_t)u : ws.ids + m.seg_off;
     for (int s = tid; s < Sp; s += blockDim.x) {
         const int id = (s < S) ? ids[s] : V;
         ids_sm[s] = id;
-        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+        if (id < V) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
     }
     __syncthreads();
     int n_kept = 0;
@@ -305,16 +307,20 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
             cur_u = u;
             m = ws.utt[u];
             in = ws.inputs[u];
-            S = m.S; Sp = m.Sp; T = m.T;
+            // compacted rows (m.Dp > 0, HfaWs::colmap): one column per distinct id instead of one per state --
+            // the column ids take the place of the phoneme ids, the row stride is Dp
+            const bool compact = m.Dp > 0;
+            S = compact ? m.Dp : m.S; Sp = compact ? m.Dp : m.Sp; T = m.T;
             const int mask_words = (V + 31) >> 5;
             if (tid < 8) mask_sm[tid] = (tid == 0) ? 1u : 0u;                // id 0 always kept (:39)
             __syncthreads();
-            const int32_t *ids = ws.ids + m.seg_off;
+            const int32_t *ids = compact ? ws.col_ids + m.seg_off + 4 * (int64_t)u : ws.ids + m.seg_off;
             for (int q = tid; q < Sp; q += blockDim.x) {
                 const int id = (q < S) ? ids[q] : V;
                 ids_sm[q] = id;
-                if (q < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+                if (id < V) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
             }
+            if (compact && tid == 0 && blk == ws.row_blocks[u]) ws.emis_mode[u] = 1;
             __syncthreads();
             n_kept = 0;
 #pragma unroll
@@ -446,18 +452,20 @@ hfa_emission_wide_kernel(HfaWs ws, int n_utt, int V, int sp_cap)
     const int u = ws.block_utt[blockIdx.x];
     const HfaUtt m = ws.utt[u];
     const HfaInput in = ws.inputs[u];
-    const int T = m.T, S = m.S, Sp = m.Sp;
+    const bool compact = m.Dp > 0;                                           // see the stream kernel
+    const int T = m.T, S = compact ? m.Dp : m.S, Sp = compact ? m.Dp : m.Sp;
     const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
     const TIn *frame = reinterpret_cast<const TIn *>(in.frame);
     float *g_out = ws.emis + m.emis_off;
+    if (compact && t_base == 0 && threadIdx.x == 0) ws.emis_mode[u] = 1;
 
     for (int w = tid; w < mask_words; w += blockDim.x) mask_sm[w] = (w == 0) ? 1u : 0u;  // id 0 (:39)
     __syncthreads();
-    const int32_t *ids = ws.ids + m.seg_off;
+    const int32_t *ids = compact ? ws.col_ids + m.seg_off + 4 * (int64_t)u : ws.ids + m.seg_off;
     for (int s = tid; s < Sp; s += blockDim.x) {
         const int id = (s < S) ? ids[s] : V;
         ids_sm[s] = id;
-        if (s < S) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
+        if (id < V) atomicOr(&mask_sm[id >> 5], 1u << (id & 31));
     }
     __syncthreads();
 
@@ -509,6 +517,7 @@ hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
     const int rows = min(HFA_EMIS_ROWS, T - t_base);
     const float *src = prob_log + m.cell_off + (int64_t)t_base * S;
     float *dst = ws.emis + m.emis_off + (int64_t)t_base * Sp;
+    if (m.Dp > 0 && t_base == 0 && tid == 0) ws.emis_mode[u] = 0;     // per-state values: plain rows
     for (int i = tid; i < rows * Sp; i += blockDim.x) {
         const int r = i / Sp, s = i - r * Sp;
         dst[i] = (s < S) ? src[(int64_t)r * S + s] : HFA_NEG_INF;
@@ -520,7 +529,32 @@ hfa_pack_kernel(HfaWs ws, int n_utt, const float *__restrict__ prob_log,
     }
 }
 
+// debug: emis[t][s] of every utterance as dense ragged [T_b][S_b] (cell_off), whatever the stored layout
+__global__ void __launch_bounds__(256)
+hfa_unpack_emis_kernel(HfaWs ws, float *__restrict__ out)
+{
+    const int u = ws.block_utt[blockIdx.x];
+    const HfaUtt m = ws.utt[u];
+    const bool compact = m.Dp > 0 && ws.emis_mode[u] != 0;
+    const int Ep = compact ? m.Dp : m.Sp, S = m.S;
+    const int t_base = (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS;
+    const int rows = min(HFA_EMIS_ROWS, m.T - t_base);
+    const uint8_t *cm = ws.colmap + m.seg_off;
+    for (int i = threadIdx.x; i < rows * S; i += blockDim.x) {
+        const int r = i / S, s = i - r * S;
+        out[m.cell_off + (int64_t)(t_base + r) * S + s] =
+            ws.emis[m.emis_off + (int64_t)(t_base + r) * Ep + (compact ? cm[s] : s)];
+    }
+}
+
 }  // namespace
+
+cudaError_t hfa_launch_unpack_emissions(const HfaLaunchCtx &c, int total_row_blocks, float *out)
+{
+    if (total_row_blocks <= 0) return cudaSuccess;
+    hfa_unpack_emis_kernel<<<total_row_blocks, 256, 0, c.stream>>>(c.ws, out);
+    return cudaGetLastError();
+}
 
 template <typename TIn>
 static cudaError_t launch_emission_t(const HfaLaunchCtx &c, int blocks, int max_sp, int64_t max_row_stride,

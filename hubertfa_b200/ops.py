@@ -72,7 +72,8 @@ class AlignPlan:
         check(self._lib.hfa_plan_routing(self._h, C.byref(out)))
         return dict(warp_utts=out[0], band_warps=out[1], band_k=out[2], big_band_warps=out[3],
                     big_band_k=out[4], cta_utts=out[5], keeps_dp=bool(out[6]), skew_d=out[7],
-                    pair_utts=int(self._lib.hfa_plan_pair_utterances(self._h)))
+                    pair_utts=int(self._lib.hfa_plan_pair_utterances(self._h)),
+                    stored_emission_bytes=int(self._lib.hfa_plan_stored_emission_bytes(self._h)))
 
     def algorithmic_bytes_fused(self, dtype: int = _lib.DTYPE_F32) -> int:
         return int(self._lib.hfa_plan_algorithmic_bytes_fused(self._h, dtype))
@@ -282,6 +283,16 @@ def unpack_kept_dp(plan: AlignPlan, workspace: torch.Tensor, utt: int) -> torch.
     with torch.cuda.device(workspace.device):
         check(_lib.load().hfa_debug_unpack_dp(plan.handle, workspace.data_ptr(), utt, out.data_ptr(),
                                               _stream_ptr()), "hfa_debug_unpack_dp")
+    return out
+
+
+def unpack_emissions(plan: AlignPlan, workspace: torch.Tensor) -> torch.Tensor:
+    """Test helper: the emissions the workspace holds as dense ragged f32 [sum T_b * S_b] (utterance b at its
+    cell offset, [T_b, S_b] row-major), whether the rows are stored plain or compacted per distinct id."""
+    out = torch.empty(max(plan.total_cells, 1), dtype=torch.float32, device=workspace.device)
+    with torch.cuda.device(workspace.device):
+        check(_lib.load().hfa_debug_unpack_emissions(plan.handle, workspace.data_ptr(), out.data_ptr(),
+                                                     _stream_ptr()), "hfa_debug_unpack_emissions")
     return out
 
 

@@ -110,6 +110,10 @@ int hfa_plan_routing(const hfa_plan *plan, int32_t out[8]);
  * {SP, phoneme} pairs so that the advance out of an SP needs no f64 arithmetic; tools/alignment_decoder.py:182-187
  * with curr == 0 at :226-228).  Chosen per utterance at hfa_plan_create. */
 int32_t hfa_plan_pair_utterances(const hfa_plan *plan);
+/* Bytes of emissions hfa_emission stores for this plan.  For the utterances of the pair layout the rows are
+ * compacted to one column per DISTINCT phoneme id (states with the same id have the same emission,
+ * prob_log[t, ids[s]], tools/alignment_decoder.py:239): fewer than the 4 bytes per DP cell of SURVEY 8(d). */
+int64_t hfa_plan_stored_emission_bytes(const hfa_plan *plan);
 
 /* Copies the plan's tables (descriptors, ids, bucket order) into the head of the workspace, zeroes
  * the banded kernel's exchange table and writes the TMA tensor maps of its emission windows (they
@@ -198,6 +202,11 @@ int hfa_debug_unpack_backptr(const hfa_plan *plan, const void *workspace, int32_
  * hfa_plan_routing out[6]) -- the production kernels' own values, unlike hfa_viterbi_forward's dp_dump.
  * HFA_ERR_UNSUPPORTED when the plan keeps no dp for this utterance. */
 int hfa_debug_unpack_dp(const hfa_plan *plan, const void *workspace, int32_t utt, float *out, void *stream);
+
+/* out: [dev] f32, dense ragged [T_b][S_b] for every utterance (the layout hfa_pack_emissions takes): the
+ * emissions the workspace currently holds (tools/alignment_decoder.py:239 prob_log[:, ph_seq_id]), whichever
+ * way the last writer stored them (plain or compacted rows). */
+int hfa_debug_unpack_emissions(const hfa_plan *plan, const void *workspace, float *out, void *stream);
 
 /* byte offset of a workspace region (tests peek at intermediate buffers through this):
  * which = 0 emissions f32 [sum T*Sp] (Sp = S rounded up to 4), 1 edge pairs f32x2 (per utterance

@@ -58,14 +58,13 @@ def emissions_of(dec, frames_dev, edges_dev, ids_list, V):
                     [e.stride(0) for e in edges_dev])
     ops.emission(ws, plan.handle, ops.TORCH_TO_DTYPE[frames_dev[0].dtype])
     torch.cuda.synchronize()
-    emis = plan.debug_region(ws, "emis").cpu().numpy()
-    edge2 = plan.debug_region(ws, "edge2").cpu().numpy()
+    emis = ops.unpack_emissions(plan, ws).cpu().numpy()     # dense [T][S] whatever the stored layout (compacted
+    edge2 = plan.debug_region(ws, "edge2").cpu().numpy()    # rows for big batches in the pair layout)
     out, eo, fo = [], 0, 0
     for t, s in zip(T, S):
-        sp = (s + 3) // 4 * 4
-        out.append((np.ascontiguousarray(emis[eo:eo + t * sp].reshape(t, sp)[:, :s]),
+        out.append((np.ascontiguousarray(emis[eo:eo + t * s].reshape(t, s)),
                     np.ascontiguousarray(edge2[fo:fo + t, 0]), np.ascontiguousarray(edge2[fo:fo + t, 1])))
-        eo += t * sp
+        eo += t * s
         fo += (t + 15) // 16 * 16
     return out
 
