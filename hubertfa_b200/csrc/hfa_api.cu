@@ -596,7 +596,10 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
             }
         for (const HfaUtt &m : p->utt)
             if (m.status == 0) p->stored_emis += (int64_t)m.T * (m.Dp > 0 ? m.Dp : m.Sp);
-        const bool old_order = std::getenv("HFA_WARP_ORDER") != nullptr;     // experiment: round 1's weights
+        // launch order = expected run time, longest first.  Measured on config 4 (B200, DP stage): all-plain batch
+        // 0.462 ms with round 1's weights T (2 + K) against 0.485 ms with the instruction counts; batch in pairs
+        // 0.388 ms with the instruction counts against 0.405 ms with T (2 + K) -- each layout keeps its winner.
+        const bool old_order = p->pair_count == 0;
         auto cost = [&](int32_t b) {
             const HfaUtt &m = p->utt[b];
             if (old_order) return (int64_t)m.T * (2 + (m.Sp + 31) / 32);
