@@ -20,13 +20,10 @@
 
 #define HFA_EMIS_ROWS 64
 
-cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
-                               float *dp_dump);
 cudaError_t hfa_launch_unpack_emissions(const HfaLaunchCtx &c, int total_row_blocks, float *out);
 cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, int max_pair_k, const int32_t *order, int n,
                                    float *dp_dump);
-cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
-                              float *dp_dump);
+cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, float *dp_dump);
 cudaError_t hfa_launch_dp_band(const HfaLaunchCtx &c, int k, int item_begin, int n_items, int32_t *ticket,
                                bool keep_dp, int64_t fused_row_stride, float *dp_dump);
 cudaError_t hfa_launch_dp_skew(const HfaLaunchCtx &c, int d, int item_begin, int n_items, int32_t *ticket,
@@ -156,7 +153,6 @@ struct hfa_plan {
     int32_t cta_max_sp = 0, max_sp = 4;
     int32_t warp_all_begin = 0, warp_all_count = 0, warp_max_k = 0;   // merged warp-kernel list
     int32_t warp_max_pair_k = 0, pair_count = 0;                     // ... of which in the SP-aware pair layout
-    int32_t lat_begin = 0, lat_count = 0, lat_max_sp = 0;            // small-batch latency routing
     // banded (halo) kernel work lists: [0] S <= 256 utterances of a small batch (latency regime,
     // 2 states per lane), [1] long phoneme sequences (S > 256, band_k[1] states per lane)
     std::vector<HfaBandItem> band_items;
@@ -362,8 +358,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         // its longest utterances.  Such batches go to the banded kernel (hfa_dp_band_kernel): every
         // utterance becomes several 2-states-per-lane warps on different SMs.  Big batches keep
         // one warp per utterance (no redundant halo work).
-        //   HFA_LATENCY_MODE = 0: never band (S <= 256) | 2: always band | 1: the older multi-warp
-        //   CTA kernel with a barrier per frame | unset: strips / bands when the batch needs <= HFA_BAND_MAX
+        //   HFA_LATENCY_MODE = 0: never band (S <= 256) | 2: always band
+        //   | unset: strips / bands when the batch needs <= HFA_BAND_MAX
         //   (default 3072) of them.   HFA_BIG_KERNEL = cta | band, HFA_BIG_K = 2|4|8.
         // Latency-regime kernel: the skewed wavefront (default; needs the TMA tensor maps) or the halo bands.
         //   HFA_LAT_KERNEL = skew | band,   HFA_SKEW_D = 2 | 3 (frames of skew per state)
@@ -383,17 +379,9 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         if (const char *e = std::getenv("HFA_BAND_MAX")) band_max = std::atoll(e);
         int lat_mode = -1;
         if (const char *e = std::getenv("HFA_LATENCY_MODE")) lat_mode = e[0] - '0';
-        std::vector<int32_t> lat, lat_band;
+        std::vector<int32_t> lat_band;
         bool hybrid = false;             // lat_band holds only the costliest utterances of a big batch
-        if (lat_mode == 1) {
-            for (int c = 2; c < HFA_NUM_CLASSES; ++c) {
-                lat.insert(lat.end(), lists[c].begin(), lists[c].end());
-                for (int32_t b : lists[c]) p->lat_max_sp = std::max(p->lat_max_sp, p->utt[b].Sp);
-                lists[c].clear();
-                p->class_count[c] = 0;
-            }
-            std::sort(lat.begin(), lat.end(), by_len);
-        } else if (lat_mode != 0) {
+        if (lat_mode != 0) {
             int64_t nb = 0;
             for (int c = 0; c < HFA_NUM_CLASSES; ++c)
                 for (int32_t b : lists[c]) nb += n_bands(b, skew_d > 0 ? 1 : 2);
@@ -421,28 +409,18 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                 // K-states-per-lane warp and holds 38 KB of shared memory.  Off by default; the knob stays.
                 double alpha = 0.0;
                 if (const char *e = std::getenv("HFA_HYBRID")) alpha = std::atof(e);
-                if (std::getenv("HFA_DP_MODE")) alpha = 0.0;       // per-class launch modes keep whole classes
                 auto ucost = [&](int32_t b) { return (int64_t)p->utt[b].T * ((p->utt[b].Sp + 31) / 32); };
                 int64_t sum_cost = 0;
                 for (int c = 0; c < HFA_NUM_CLASSES; ++c)
                     for (int32_t b : lists[c]) sum_cost += ucost(b);
                 const double thresh = alpha * (double)sum_cost / (4.0 * sm_count());
-                // HFA_HYBRID_KIND=cta: the same utterances go to the multi-warp CTA kernel instead (2 states per
-                // lane, one barrier per frame)
-                const char *kind = std::getenv("HFA_HYBRID_KIND");
-                const bool to_cta = kind && kind[0] == 'c';
                 if (alpha > 0.0) {
                     int64_t strips = 0;
-                    for (int c = (to_cta ? 2 : 1); c < HFA_NUM_CLASSES; ++c) {   // class 0 (S <= 32) is a single strip anyway
+                    for (int c = 1; c < HFA_NUM_CLASSES; ++c) {   // class 0 (S <= 32) is a single strip anyway
                         std::vector<int32_t> keep;
                         for (int32_t b : lists[c]) {
                             if ((double)ucost(b) >= thresh && strips + n_bands(b, 1) <= 8 * band_max) {
-                                if (to_cta) {
-                                    lat.push_back(b);
-                                    p->lat_max_sp = std::max(p->lat_max_sp, p->utt[b].Sp);
-                                } else {
-                                    lat_band.push_back(b);
-                                }
+                                lat_band.push_back(b);
                                 strips += n_bands(b, 1);
                             } else {
                                 keep.push_back(b);
@@ -452,7 +430,6 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
                         p->class_count[c] = (int32_t)lists[c].size();
                     }
                     std::sort(lat_band.begin(), lat_band.end(), by_len);
-                    std::sort(lat.begin(), lat.end(), by_len);
                     hybrid = !lat_band.empty();
                 }
             }
@@ -537,10 +514,8 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         // So: if the frames-weighted instruction count of the possible utterances is lower in pairs, all of them
         // go there.  Instructions per frame counted in the SASS (loop bodies + the per-tile work / 8):
         // 16 + 21 K plain, 17 + 25 KP in pairs.   HFA_PAIR = 0: never | 2: whenever possible | unset: as above.
-        // Only in the merged launch (the per-class launch modes keep the plain bodies).
         int pair_mode = 1;
         if (const char *e = std::getenv("HFA_PAIR")) pair_mode = std::atoi(e);
-        if (std::getenv("HFA_DP_MODE")) pair_mode = 0;
         std::vector<int32_t> warp_all;
         std::vector<std::pair<int32_t, int>> pairable;          // (utterance, pairs per lane)
         int64_t sum_pair = 0, sum_plain = 0;
@@ -610,9 +585,6 @@ int hfa_plan_create(int32_t n_utt, int32_t vocab_size, const int32_t *T, const i
         p->warp_all_begin = (int32_t)p->order.size();
         p->warp_all_count = (int32_t)warp_all.size();
         p->order.insert(p->order.end(), warp_all.begin(), warp_all.end());
-        p->lat_begin = (int32_t)p->order.size();
-        p->lat_count = (int32_t)lat.size();
-        p->order.insert(p->order.end(), lat.begin(), lat.end());
         std::sort(all.begin(), all.end(), by_len);
         p->bt_begin = (int32_t)p->order.size();
         p->order.insert(p->order.end(), all.begin(), all.end());
@@ -747,7 +719,7 @@ int hfa_plan_routing(const hfa_plan *p, int32_t out[8])
     out[2] = p->band_k[0];
     out[3] = p->band_count[1];
     out[4] = p->band_k[1];
-    out[5] = p->lat_count + p->class_count[HFA_NUM_CLASSES];
+    out[5] = p->class_count[HFA_NUM_CLASSES];
     out[6] = p->dp_store_elems > 0;
     out[7] = std::max(p->band_skew[0], p->band_skew[1]);
     return HFA_OK;
@@ -940,20 +912,6 @@ int hfa_pack_emissions(const hfa_plan *p, void *workspace, const float *prob_log
     return HFA_OK;
 }
 
-// HFA_DP_MODE=merged (default): every warp-kernel state class in one launch.
-// HFA_DP_MODE=streams: one launch per class, forked onto side streams and joined.
-// HFA_DP_MODE=serial: one launch per class on the caller's stream.
-static int dp_mode()
-{
-    static const int mode = [] {
-        const char *e = std::getenv("HFA_DP_MODE");
-        if (e && std::strcmp(e, "streams") == 0) return 1;
-        if (e && std::strcmp(e, "serial") == 0) return 2;
-        return 0;
-    }();
-    return mode;
-}
-
 // fused_row_stride > 0 (hfa_align_batch only): every utterance is in the banded kernel and the
 // producer warps compute the emissions from the logits themselves
 static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_dump, void *stream,
@@ -961,27 +919,19 @@ static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_du
 {
     if (!p || !workspace) return fail(HFA_ERR_ARG, "hfa_viterbi_forward: NULL plan/workspace");
     HfaLaunchCtx c = make_ctx(p, workspace, stream);
-    const int mode = dp_mode();
     const int n_cta = p->class_count[HFA_NUM_CLASSES];
-    // launches of this call: (merged ? 1 : one per class) + the CTA-per-utterance kernel
+    // launches of this call: the merged warp kernel (every state class in one launch), the strips / bands of the
+    // two lists, the CTA-per-utterance kernel -- forked onto side streams when there is more than one
     struct Item { int k; const int32_t *order; int n; };
-    Item items[HFA_NUM_CLASSES + 4];
+    Item items[4];
     int n_items = 0;
-    if (mode == 0) {
-        if (p->warp_all_count > 0)
-            items[n_items++] = {0, c.ws.order + p->warp_all_begin, p->warp_all_count};
-    } else {
-        for (int k = 0; k < HFA_NUM_CLASSES; ++k)
-            if (p->class_count[k] > 0)
-                items[n_items++] = {k + 1, c.ws.order + p->class_begin[k], p->class_count[k]};
-    }
+    if (p->warp_all_count > 0) items[n_items++] = {0, c.ws.order + p->warp_all_begin, p->warp_all_count};
     if (p->band_count[0] > 0) items[n_items++] = {-3, nullptr, 0};
-    if (p->lat_count > 0) items[n_items++] = {-2, c.ws.order + p->lat_begin, p->lat_count};
     if (p->band_count[1] > 0) items[n_items++] = {-4, nullptr, 1};
     if (n_cta > 0) items[n_items++] = {-1, c.ws.order + p->class_begin[HFA_NUM_CLASSES], n_cta};
     if (n_items == 0) return HFA_OK;
 
-    const bool fork = n_items > 1 && mode != 2;
+    const bool fork = n_items > 1;
     HfaSideStreams *ss = nullptr;
     if (fork) {
         ss = side_streams();
@@ -1000,8 +950,6 @@ static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_du
         }
         if (items[it].k == 0)
             e = hfa_launch_dp_warp_any(c, p->warp_max_k, p->warp_max_pair_k, items[it].order, items[it].n, dp_dump);
-        else if (items[it].k > 0)
-            e = hfa_launch_dp_warp(c, items[it].k, items[it].order, items[it].n, dp_dump);
         else if (items[it].k == -3 || items[it].k == -4) {
             const int wh = items[it].k == -3 ? 0 : 1;
             if (p->band_skew[wh] > 0)
@@ -1011,10 +959,8 @@ static int viterbi_forward_impl(const hfa_plan *p, void *workspace, float *dp_du
                 e = hfa_launch_dp_band(c, p->band_k[wh], p->band_begin[wh], p->band_count[wh],
                                        c.ws.band_ticket + wh, p->dp_store_elems > 0, fused_row_stride, dp_dump);
         }
-        else if (items[it].k == -2)
-            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->lat_max_sp, 2, dp_dump);
         else
-            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->cta_max_sp, HFA_CTA_K, dp_dump);
+            e = hfa_launch_dp_cta(c, items[it].order, items[it].n, p->cta_max_sp, dp_dump);
         if (e != cudaSuccess) return cuda_fail(e, "hfa_viterbi_forward: kernel launch");
         g_launches += 1;
         if (side) {
@@ -1058,7 +1004,7 @@ int hfa_backtrace(const hfa_plan *p, void *workspace, void *result, float *frame
 static bool fused_ok(const hfa_plan *p, const void *workspace, int32_t dtype)
 {
     const int64_t max_row_stride = p->row_stride_of(workspace);
-    const bool all_banded = p->warp_all_count == 0 && p->lat_count == 0 &&
+    const bool all_banded = p->warp_all_count == 0 &&
                             p->class_count[HFA_NUM_CLASSES] == 0 && !p->band_items.empty();
     const bool skewed = p->band_skew[0] > 0 || p->band_skew[1] > 0;   // no producer warp there to fuse into
     return all_banded && !skewed && p->dp_store_elems > 0 && dtype == HFA_DTYPE_F32 && max_row_stride > 0 &&

@@ -674,15 +674,6 @@ __device__ __forceinline__ void hfa_dp_pair_body(const HfaWs &ws, const int u, f
     }
 }
 
-// one state class per launch (used when the classes are spread over streams)
-template <int K, bool DUMP>
-__global__ void __launch_bounds__(32)
-hfa_dp_warp_kernel(HfaWs ws, const int32_t *__restrict__ order, float *__restrict__ dp_dump)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    hfa_dp_warp_body<K, DUMP>(ws, order[blockIdx.x], dp_dump, smem_raw);
-}
-
 // every state class in ONE launch: each warp picks the code path of its utterance.  All warps get
 // the shared memory of the largest class present, the block scheduler sees one globally
 // longest-first ordered grid, and nothing depends on concurrent-kernel scheduling.  WPC warps per
@@ -851,181 +842,6 @@ hfa_dp_cta_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int s
         // for a tile that only holds frame 0, before this point): one more barrier frees the stage.
         cta_sync();
         if (tid == 0 && i + HFA_CTA_STAGES < n_tiles) issue(i + HFA_CTA_STAGES);
-    }
-    if (T == 1) hfa_store_bits<K>(g_bp + first, bits, first, Sp);   // row 0 word (all zero)
-
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if (first + k == S - 1) ws.dp_last[2 * u] = dp[k];
-        if (first + k == S - 2) ws.dp_last[2 * u + 1] = dp[k];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// CTA per utterance, skewed wavefront (256 < S <= 8192; BASELINE config 3).
-// Warp w owns states [256 w, 256 w + 256), 8 per lane.  Instead of a CTA barrier per frame, warp w
-// publishes the two advance scores its right neighbour needs into a 64-slot shared-memory ring and
-// bumps a flag; warp w+1 spins on that flag only.  Warp 0 never waits, so the warps settle into a
-// one-frame-per-warp skew and every warp runs at its own issue rate.  Emission tiles arrive by TMA
-// through a full/empty mbarrier pipeline (3 stages); lane 0 of warp 0 is the producer and only ever
-// polls the "empty" barrier (test_wait), it never blocks on slower warps.  A warp can lead its right
-// neighbour by at most 3 stages x tile_t <= 48 frames < 64 ring slots.
-// ---------------------------------------------------------------------------------------------
-constexpr int HFA_WAVE_RING = 64;
-
-template <int K, int NT>
-__global__ void __launch_bounds__(NT)
-hfa_dp_wave_kernel(HfaWs ws, const int32_t *__restrict__ order, int tile_t, int stage_floats,
-                   float *__restrict__ dp_dump)
-{
-    constexpr int NST = HFA_CTA_STAGES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [stages x stage_floats f32][one slack row][stages x 16 float2][full, empty mbarriers]
-    // [32 x 64 float2 ring][32 flags]
-    float *tile0 = reinterpret_cast<float *>(smem_raw);
-    float2 *edge0 = reinterpret_cast<float2 *>(tile0 + NST * stage_floats + stage_floats / tile_t);
-    uint64_t *full = reinterpret_cast<uint64_t *>(edge0 + NST * HFA_TILE_T);
-    uint64_t *empty = full + NST;
-    float2 *ring = reinterpret_cast<float2 *>(empty + NST);
-    volatile int *flag = reinterpret_cast<volatile int *>(ring + 32 * HFA_WAVE_RING);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = order[blockIdx.x];
-    const HfaUtt m = ws.utt[u];
-    const int T = m.T, S = m.S, Sp = m.Sp;
-    const int nw = (Sp + 32 * K - 1) / (32 * K);               // warps that own states
-    const int first = tid * K;
-    const int n_tiles = (T + tile_t - 1) / tile_t;
-    const float *g_emis = ws.emis + m.emis_off;
-    const float2 *g_edge = ws.edge2 + m.edge_off;
-    uint32_t *g_bp = ws.bp + m.bp_off;
-    const double ratio = __ddiv_rn((double)T, (double)S);
-    constexpr uint32_t edge_bytes = HFA_TILE_T * (uint32_t)sizeof(float2);
-
-    auto issue = [&](int i) {                                  // lane 0 of warp 0 only
-        const int st = i % NST;
-        const int t0 = i * tile_t;
-        const int rows = min(tile_t, T - t0);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)Sp * 4u;
-        hfa_mbar_expect_tx(&full[st], bytes + edge_bytes);
-        hfa_bulk_load(tile0 + st * stage_floats, g_emis + (int64_t)t0 * Sp, bytes, &full[st]);
-        hfa_bulk_load(edge0 + st * HFA_TILE_T, g_edge + (t0 & ~(HFA_TILE_T - 1)), edge_bytes, &full[st]);
-    };
-    int next_issue = 0;                                        // producer state (thread 0)
-    if (tid == 0) {
-        for (int s = 0; s < NST; ++s) {
-            hfa_mbar_init(&full[s], 1);
-            hfa_mbar_init(&empty[s], (uint32_t)nw);
-        }
-        hfa_fence_mbar_init();
-        for (; next_issue < NST && next_issue < n_tiles; ++next_issue) issue(next_issue);
-    }
-    if (tid < 32) flag[tid] = 0;
-    __syncthreads();
-    if (warp >= nw) return;                                    // warps without states of THIS utterance
-
-    uint32_t sp_and[K];
-    float jump_cap[K];
-    hfa_state_masks<K>(ws.ids + m.seg_off, first, S, sp_and, jump_cap);
-    const bool lead_sp = (ws.ids[m.seg_off] == 0) && (S > 1);
-    float dp[K], cu[K];
-    uint32_t bits[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        dp[k] = HFA_NEG_INF;
-        cu[k] = HFA_NEG_INF;
-        bits[k] = 0;
-    }
-    float2 *my_ring = ring + warp * HFA_WAVE_RING;
-    const float2 *left_ring = ring + (warp > 0 ? warp - 1 : 0) * HFA_WAVE_RING;
-
-    for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % NST;
-        // the producer must have issued tile i before anybody (itself included) waits for it; only
-        // here may it block on slower warps -- they never wait for anything warp 0 has not done yet
-        if (tid == 0) {
-            while (next_issue <= i) {
-                hfa_mbar_wait(&empty[next_issue % NST], (uint32_t)(((next_issue / NST) - 1) & 1));
-                issue(next_issue);
-                ++next_issue;
-            }
-        }
-        hfa_mbar_wait(&full[st], (uint32_t)((i / NST) & 1));
-        const float *tl = tile0 + st * stage_floats + (first < Sp ? first : 0);
-        const float2 *et = edge0 + st * HFA_TILE_T;
-        const int rows = min(tile_t, T - i * tile_t);
-        float e[K];
-        hfa_load_row<K>(tl, e);
-        for (int tt = 0; tt < rows; ++tt) {
-            const int t = i * tile_t + tt;
-            // producer duty: re-issue a stage as soon as every warp has released it (never blocks)
-            if (tid == 0 && next_issue < n_tiles &&
-                hfa_mbar_test_wait(&empty[next_issue % NST], (uint32_t)(((next_issue / NST) - 1) & 1))) {
-                issue(next_issue);
-                ++next_issue;
-            }
-            float en[K];
-            hfa_load_row<K>(tl + (tt + 1) * Sp, en);        // next frame's operands (slack row at the end)
-            if (t == 0) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int s = first + k;
-                    if (s == 0 || (s == 1 && lead_sp)) {
-                        dp[k] = e[k];
-                        cu[k] = e[k];
-                    }
-                    if (dp_dump != nullptr && s < S) dp_dump[m.cell_off + s] = dp[k];
-                }
-            } else {
-                const float2 ed = et[t & (HFA_TILE_T - 1)];
-                float stay[K], adv[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float base = __fadd_rn(dp[k], e[k]);
-                    stay[k] = __fadd_rn(base, ed.y);
-                    adv[k] = hfa_advance(__fadd_rn(base, ed.x), cu[k], ratio);
-                }
-                float up1 = __shfl_up_sync(0xffffffffu, adv[K - 1], 1);
-                float up2 = __shfl_up_sync(0xffffffffu, adv[K - 2], 1);
-                if (lane == 31 && warp + 1 < nw) {           // publish for the right neighbour
-                    my_ring[t & (HFA_WAVE_RING - 1)] = make_float2(adv[K - 1], adv[K - 2]);
-                    __threadfence_block();
-                    flag[warp] = t;
-                }
-                if (lane == 0) {
-                    if (warp == 0) {
-                        up1 = HFA_NEG_INF;
-                        up2 = HFA_NEG_INF;
-                    } else {
-                        uint32_t spins = 0;
-                        while (flag[warp - 1] < t)
-                            if (++spins > (1u << 26)) __trap();
-                        __threadfence_block();
-                        const float2 v = left_ring[t & (HFA_WAVE_RING - 1)];
-                        up1 = v.x;
-                        up2 = v.y;
-                    }
-                }
-                __syncwarp();
-                const int b = t & 15;
-                hfa_select<K>(e, stay, adv, up1, up2, sp_and, jump_cap, 1u << b, 0x10000u << b, dp, cu, bits);
-                if (dp_dump != nullptr) {
-                    const int64_t o = m.cell_off + (int64_t)t * S;
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        if (first + k < S) dp_dump[o + first + k] = dp[k];
-                }
-                if (b == 15 || t == T - 1) {
-                    hfa_store_bits<K>(g_bp + (int64_t)(t >> 4) * Sp + first, bits, first, Sp);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) bits[k] = 0;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) e[k] = en[k];
-        }
-        __syncwarp();
-        if (lane == 0) hfa_mbar_arrive(&empty[st]);          // this warp is done with stage st
     }
     if (T == 1) hfa_store_bits<K>(g_bp + first, bits, first, Sp);   // row 0 word (all zero)
 
@@ -1494,26 +1310,6 @@ hfa_dp_band_kernel(HfaWs ws, int item_begin, int32_t *ticket, float *__restrict_
     }
 }
 
-template <int K>
-cudaError_t launch_warp(const HfaLaunchCtx &c, const int32_t *order, int n, float *dp_dump)
-{
-    if (n <= 0) return cudaSuccess;
-    const size_t smem = hfa_warp_smem_bytes<K>();
-    cudaError_t e;
-    if (dp_dump != nullptr) {
-        e = cudaFuncSetAttribute(hfa_dp_warp_kernel<K, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hfa_dp_warp_kernel<K, true><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
-    } else {
-        e = cudaFuncSetAttribute(hfa_dp_warp_kernel<K, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hfa_dp_warp_kernel<K, false><<<n, 32, smem, c.stream>>>(c.ws, order, dp_dump);
-    }
-    return cudaGetLastError();
-}
-
 }  // namespace
 
 template <bool DUMP, int MAXK>
@@ -1549,34 +1345,16 @@ cudaError_t hfa_launch_dp_warp_any(const HfaLaunchCtx &c, int max_k, int max_pai
     return launch_any<false, 8>(c, smem, order, n, dp_dump);
 }
 
-// order: device pointer to the utterance indices of this class; n: how many
-cudaError_t hfa_launch_dp_warp(const HfaLaunchCtx &c, int K, const int32_t *order, int n,
-                               float *dp_dump)
-{
-    switch (K) {
-        case 1: return launch_warp<1>(c, order, n, dp_dump);
-        case 2: return launch_warp<2>(c, order, n, dp_dump);
-        case 3: return launch_warp<3>(c, order, n, dp_dump);
-        case 4: return launch_warp<4>(c, order, n, dp_dump);
-        case 5: return launch_warp<5>(c, order, n, dp_dump);
-        case 6: return launch_warp<6>(c, order, n, dp_dump);
-        case 7: return launch_warp<7>(c, order, n, dp_dump);
-        case 8: return launch_warp<8>(c, order, n, dp_dump);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-// all utterances of a CTA-per-utterance list share one launch; max_sp = largest padded S among them,
-// k = states per thread (8: long phoneme sequences; 2: the small-batch "latency" routing, where an
-// utterance gets ceil(Sp/64) warps instead of one so that its serial chain issues fewer
-// instructions per frame)
-cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, int k,
-                              float *dp_dump)
+// all utterances of the CTA-per-utterance list share one launch; max_sp = largest padded S among them
+// (8 states per thread, one bar.sync per frame).  Round 1 also had a flag-synchronised wavefront variant of this
+// kernel and a 2-states-per-thread "latency" variant: both lost to the strips of hfa_dp_skew.cu (config 3:
+// 16.9 / 17.8 ms against 1.62 ms) and were removed in round 2.
+cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n, int max_sp, float *dp_dump)
 {
     if (n <= 0) return cudaSuccess;
-    int threads = (max_sp + k - 1) / k;
+    int threads = (max_sp + HFA_CTA_K - 1) / HFA_CTA_K;
     threads = ((threads + 31) / 32) * 32;
-    if (threads > 1024 || (k != 2 && k != HFA_CTA_K)) return cudaErrorInvalidValue;
+    if (threads > 1024) return cudaErrorInvalidValue;
     // frames per stage: largest power of two <= 16 whose stage stays under ~64 KB
     int tile_t = HFA_TILE_T;
     while (tile_t > 1 && (size_t)tile_t * max_sp * sizeof(float) > 64 * 1024) tile_t >>= 1;
@@ -1585,46 +1363,15 @@ cudaError_t hfa_launch_dp_cta(const HfaLaunchCtx &c, const int32_t *order, int n
                         HFA_CTA_STAGES * HFA_TILE_T * sizeof(float2) +
                         HFA_CTA_STAGES * sizeof(uint64_t) + 2 * 32 * sizeof(float2);
     cudaError_t e;
-#define HFA_CTA_LAUNCH(KK, NT)                                                                     \
-    e = cudaFuncSetAttribute(hfa_dp_cta_kernel<KK, NT>,                                            \
+#define HFA_CTA_LAUNCH(NT)                                                                         \
+    e = cudaFuncSetAttribute(hfa_dp_cta_kernel<HFA_CTA_K, NT>,                                     \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
     if (e != cudaSuccess) return e;                                                                \
-    hfa_dp_cta_kernel<KK, NT><<<n, threads, smem, c.stream>>>(c.ws, order, tile_t, stage_floats,   \
-                                                             dp_dump)
-    const char *lat_env = getenv("HFA_LATENCY_KERNEL");
-    if (k == 2 && lat_env && lat_env[0] == 'b') {       // barrier variant of the latency routing
-        if (threads > 128) return cudaErrorInvalidValue;
-        HFA_CTA_LAUNCH(2, 128);
-        return cudaGetLastError();
-    }
-    // Default: one bar.sync per frame.  HFA_CTA_WAVE=1 selects the skewed-wavefront kernel below; on
-    // B200 both take ~1100 cycles per frame for S = 2000 (16.9 vs 17.8 ms on config 3): the frame
-    // time is the instruction stream of 2000 states on ONE SM, not the synchronisation.
-    const char *wave_env = getenv("HFA_CTA_WAVE");
-    if (k != 2 && !(wave_env && wave_env[0] == '1')) {
-        if (threads <= 256) { HFA_CTA_LAUNCH(HFA_CTA_K, 256); }
-        else if (threads <= 512) { HFA_CTA_LAUNCH(HFA_CTA_K, 512); }
-        else { HFA_CTA_LAUNCH(HFA_CTA_K, 1024); }
-        return cudaGetLastError();
-    }
+    hfa_dp_cta_kernel<HFA_CTA_K, NT><<<n, threads, smem, c.stream>>>(c.ws, order, tile_t, stage_floats, dp_dump)
+    if (threads <= 256) { HFA_CTA_LAUNCH(256); }
+    else if (threads <= 512) { HFA_CTA_LAUNCH(512); }
+    else { HFA_CTA_LAUNCH(1024); }
 #undef HFA_CTA_LAUNCH
-    // skewed-wavefront kernel: one extra stage-sized slack row block for the operand prefetch
-    const size_t wsmem = ((size_t)HFA_CTA_STAGES * stage_floats + max_sp) * sizeof(float) +
-                         HFA_CTA_STAGES * HFA_TILE_T * sizeof(float2) + 2 * HFA_CTA_STAGES * sizeof(uint64_t) +
-                         32 * HFA_WAVE_RING * sizeof(float2) + 32 * sizeof(int);
-#define HFA_WAVE_LAUNCH(KK, NT)                                                                    \
-    e = cudaFuncSetAttribute(hfa_dp_wave_kernel<KK, NT>,                                           \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);             \
-    if (e != cudaSuccess) return e;                                                                \
-    hfa_dp_wave_kernel<KK, NT><<<n, threads, wsmem, c.stream>>>(c.ws, order, tile_t, stage_floats, \
-                                                               dp_dump)
-    if (k == 2) {
-        if (threads > 128) return cudaErrorInvalidValue;
-        HFA_WAVE_LAUNCH(2, 128);
-    } else if (threads <= 256) { HFA_WAVE_LAUNCH(HFA_CTA_K, 256); }
-    else if (threads <= 512) { HFA_WAVE_LAUNCH(HFA_CTA_K, 512); }
-    else { HFA_WAVE_LAUNCH(HFA_CTA_K, 1024); }
-#undef HFA_WAVE_LAUNCH
     return cudaGetLastError();
 }
 

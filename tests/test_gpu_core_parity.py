@@ -11,14 +11,14 @@ from oracle import hfa_oracle_np as onp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "0p2", "0p0", "1", "2k4", "2k8", "2nk", "2rc", "2s2", "2s3", "2s2slow", "2s2nk", "auto"],
-                ids=["warp-per-utterance", "warp-pair-layout-forced", "warp-plain-layout-only", "cta-latency-routing", "banded-k2-k4", "banded-k2-k8",
+@pytest.fixture(params=["0", "0p2", "0p0", "2k4", "2k8", "2nk", "2rc", "2s2", "2s3", "2s2slow", "2s2nk", "auto"],
+                ids=["warp-per-utterance", "warp-pair-layout-forced", "warp-plain-layout-only", "banded-k2-k4", "banded-k2-k8",
                      "banded-no-dp-store", "banded-row-copies", "skew-d2", "skew-d3", "skew-d2-guarded-body",
                      "skew-d2-no-dp-store", "auto"])
 def routing(request, monkeypatch):
     """HFA_LATENCY_MODE: 0 = every S <= 256 utterance in the warp kernel (all 8 state classes) and
     S > 256 in the CTA kernel -- the SP-aware pair layout where the plan's cost rule picks it, wherever it is
-    possible (HFA_PAIR=2) or nowhere (HFA_PAIR=0); 1 = utterances with > 64 states go to the multi-warp CTA kernel;
+    possible (HFA_PAIR=2) or nowhere (HFA_PAIR=0);
     2 = everything in the banded (halo) kernel, S > 256 with 4 / 8 states per lane, the backtrace
     reading the dp the forward pass kept -- or (no-dp-store) re-scoring the path, or (row-copies)
     without the TMA tensor maps; skew-* = everything (S > 256 included) in the skewed-wavefront kernel
@@ -88,11 +88,13 @@ def test_random_shapes_all_classes(routing):
             raise AssertionError(f"shape {shp}: {e}") from e
 
 
-def test_wavefront_cta_kernel(monkeypatch):
-    """HFA_CTA_WAVE=1: the flag-synchronised (barrier-free) variant of the CTA-per-utterance kernel."""
-    monkeypatch.setenv("HFA_CTA_WAVE", "1")
+def test_cta_per_utterance_kernel(monkeypatch):
+    """S > 256 in a batch that is never cut into strips: the CTA-per-utterance kernel (8 states per thread, one
+    barrier per frame), 256 / 512 / 1024 threads."""
+    monkeypatch.setenv("HFA_LATENCY_MODE", "0")
+    monkeypatch.setenv("HFA_BIG_KERNEL", "cta")
     shapes = [(600, 257, "alternate"), (700, 300, "alternate"), (1000, 513, "alternate"),
-              (1300, 1030, "alternate"), (50, 2100, "dictionary"), (1, 300, "alternate")]
+              (1300, 1030, "alternate"), (50, 2100, "dictionary"), (1, 300, "alternate"), (40, 5000, "dictionary")]
     ins = [synth_core_inputs(T, S, 63, 7000 + i, style, planted=bool(i % 2)) for i, (T, S, style) in enumerate(shapes)]
     out = run_core_gpu([x["ids"] for x in ins], [x["prob_log"] for x in ins], [x["el"] for x in ins],
                        [x["ne"] for x in ins], [x["p"] for x in ins], 0.02)

@@ -74,8 +74,11 @@ def test_pair_layout_is_chosen_for_the_batch(monkeypatch):
     monkeypatch.setenv("HFA_PAIR", "0")
     assert mk(dictionary).routing()["pair_utts"] == 0
     monkeypatch.delenv("HFA_PAIR")
-    monkeypatch.setenv("HFA_DP_MODE", "serial")        # the per-class launch modes keep the plain bodies
-    assert mk(dictionary).routing()["pair_utts"] == 0
+    big = ops.AlignPlan([100] * 3, [40, 30, 255], np.concatenate(dictionary[:3]), 300, 0.02)   # V > 255: plain rows
+    assert big.routing()["pair_utts"] == 3
+    assert big.routing()["stored_emission_bytes"] == 4 * 100 * (40 + 32 + 256)
+    r = mk(dictionary).routing()                         # alt(): two distinct ids -> 4 columns instead of 40 / 32 / 256
+    assert r["stored_emission_bytes"] == 4 * 100 * (4 + 4 + 4 + 64 + 200)
 
 
 def test_compute_entry_points_fail_loudly_without_cuda():
