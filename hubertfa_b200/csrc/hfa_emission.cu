@@ -49,6 +49,29 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     return v;
 }
 
+// One edge logit per frame out of a [T, V+2] head output is a 4-byte load every row stride: by default the L2
+// fetches the whole 128-byte line around it from HBM (ncu, config 4: 460 MB read for 3.7 M frames).  The 64-byte
+// fetch-granularity hint is the smallest PTX offers; the rest of the line belongs to the emission kernel's copy.
+template <typename TIn> __device__ __forceinline__ float hfa_ld_edge(const TIn *p);
+template <> __device__ __forceinline__ float hfa_ld_edge<float>(const float *p)
+{
+    float v;
+    asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <> __device__ __forceinline__ float hfa_ld_edge<__half>(const __half *p)
+{
+    unsigned short v;
+    asm volatile("ld.global.L2::64B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __half2float(__ushort_as_half(v));
+}
+template <> __device__ __forceinline__ float hfa_ld_edge<__nv_bfloat16>(const __nv_bfloat16 *p)
+{
+    unsigned short v;
+    asm volatile("ld.global.L2::64B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __bfloat162float(__ushort_as_bfloat16(v));
+}
+
 // edge stream of one CTA's 64 frames, one thread per frame (:68-71,:84,:241-242)
 template <typename TIn>
 __device__ __forceinline__ void edge_block(const HfaWs &ws, const HfaUtt &m, const HfaInput &in,
@@ -58,9 +81,8 @@ __device__ __forceinline__ void edge_block(const HfaWs &ws, const HfaUtt &m, con
         const int t = t_base + tid;
         if (t < m.T) {
             const TIn *edge = reinterpret_cast<const TIn *>(in.edge);
-            const float p = edge_pred(hfa_to_float<TIn>(edge[(int64_t)t * in.edge_st]));
-            const float pp =
-                (t > 0) ? edge_pred(hfa_to_float<TIn>(edge[(int64_t)(t - 1) * in.edge_st])) : 0.0f;
+            const float p = edge_pred(hfa_ld_edge<TIn>(edge + (int64_t)t * in.edge_st));
+            const float pp = (t > 0) ? edge_pred(hfa_ld_edge<TIn>(edge + (int64_t)(t - 1) * in.edge_st)) : 0.0f;
             float2 lg;
             edge_logs(p, pp, lg);
             ws.edge2[m.edge_off + t] = lg;
