@@ -224,8 +224,8 @@ hfa_backtrace_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, HfaResu
         const int t = min(round * 32 + lane, T - 1);         // clamped: always a valid address
         const float *row = emis + (int64_t)t * Ep;
         Raw g;
-        g.x = row[compact ? (int)cmap[st] : st];
-        g.y = row[compact ? (int)cmap[sprev] : sprev];
+        g.x = hfa_ldg_f32_64B(row + (compact ? (int)cmap[st] : st));
+        g.y = hfa_ldg_f32_64B(row + (compact ? (int)cmap[sprev] : sprev));
         g.ed = edge2[t];
         g.id = ids[st];
         g.st = st;
@@ -478,8 +478,8 @@ hfa_backtrace_tables_kernel(HfaWs ws, const int32_t *__restrict__ order, int n, 
 #pragma unroll
             for (int f = 0; f < 16; ++f) {
                 const int t = min(16 * wr + f, T - 1);
-                dv[f] = dps[m.skew_d > 0 ? hfa_skew_dp_index(m.skew_d, T, t, path_state[t])
-                                         : hfa_dp_store_index(m.band_k, T, t, path_state[t])];
+                dv[f] = hfa_ldg_f32_64B(dps + (m.skew_d > 0 ? hfa_skew_dp_index(m.skew_d, T, t, path_state[t])
+                                                            : hfa_dp_store_index(m.band_k, T, t, path_state[t])));
             }
 #pragma unroll
             for (int f = 0; f < 16; ++f)

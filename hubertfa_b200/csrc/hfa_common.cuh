@@ -241,6 +241,15 @@ __device__ __forceinline__ void hfa_mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// Scattered 4-byte gathers (one value out of a row or a column per frame): by default the L2 fetches the whole
+// 128-byte line from HBM; the 64-byte fetch-granularity hint (SASS: LDG.E.LTC64B) is the smallest PTX offers.
+__device__ __forceinline__ float hfa_ldg_f32_64B(const float *p)
+{
+    float v;
+    asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // the one mixed-precision operation of the recurrence (alignment_decoder.py:182-187):
 // f32( f64(a) + f64(curr) * ratio ), multiply and add rounded separately (no FMA contraction).
 __device__ __forceinline__ float hfa_advance(float a, float curr, double ratio)
