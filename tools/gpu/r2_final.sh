@@ -1,6 +1,6 @@
 # round-2 final measurements on one B200 (plain runs first, then the ncu passes of the same commands)
-mkdir -p gpurun_out/r2
-O=gpurun_out/r2
+mkdir -p gpurun_out/r2z
+O=gpurun_out/r2z
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/gpu_tests.log 2>&1; echo "tests rc=$?"; tail -2 $O/gpu_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
 timeout 900 python bench.py > $O/bench_c2.json 2> $O/bench_c2.err; echo "bench rc=$?"
@@ -10,20 +10,9 @@ timeout 300 python bench.py --workload c3 --no-extra --steps 30 --cpu-seconds 5 
 timeout 300 python bench.py --workload c4 --no-extra --no-cpu --steps 20 > $O/bench_c4.json 2> $O/bench_c4.err
 timeout 300 python bench.py --workload c4j --no-extra --no-cpu --steps 20 > $O/bench_c4j.json 2> $O/bench_c4j.err
 timeout 300 python tools/time_decode.py > $O/time_decode.log 2>&1; tail -3 $O/time_decode.log
-# ncu: launch list, then full captures of one step's kernels (eager launches so that every kernel is a launch)
-python bench.py --no-cpu --no-extra --no-graph --steps 3 --warmup 3 > $O/plain_c2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/launches_c2.csv \
-    python bench.py --no-cpu --no-extra --no-graph --steps 3 --warmup 3 > $O/ncu_list_c2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:hfa_ -s 15 -c 5 -o $O/prof_c2 -f \
-    python bench.py --no-cpu --no-extra --no-graph --steps 3 --warmup 3 > $O/ncu_full_c2.log 2>&1
-tail -1 $O/ncu_full_c2.log | cut -c1-160
-python bench.py --workload c4 --no-cpu --no-extra --steps 2 --warmup 3 > $O/plain_c4.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:hfa_ -s 12 -c 4 -o $O/prof_c4 -f \
-    python bench.py --workload c4 --no-cpu --no-extra --steps 2 --warmup 3 > $O/ncu_full_c4.log 2>&1
-tail -1 $O/ncu_full_c4.log | cut -c1-160
 python - <<'PY'
 import json
-O="gpurun_out/r2"
+O="gpurun_out/r2z"
 for f in ["c2","reference_arm","c1","c3","c4","c4j"]:
     try:
         d=json.loads(open(f"{O}/bench_{f}.json").read().strip().splitlines()[-1])
