@@ -256,6 +256,27 @@ hfa_edge_kernel(HfaWs ws)
     edge_block<TIn>(ws, m, in, (blockIdx.x - ws.row_blocks[u]) * HFA_EMIS_ROWS, threadIdx.x);
 }
 
+// max and sum of exp over the kept ids of one row, the part of one of the row's 4 lanes: kept id `part + 4 j` sits
+// in kreg[j].  The two 2-step butterflies that combine the 4 lanes follow in the caller.
+template <int NJ, typename TIn>
+__device__ __forceinline__ void hfa_row_stats(const TIn *row, const int (&kreg)[16], int part, int n_kept,
+                                              float &mx, float &sum)
+{
+    float xv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {           // unconditional load (kreg is 0 past the end) + select:
+        const float x = hfa_to_float<TIn>(row[kreg[j]]);          // no divergent branches
+        xv[j] = (part + 4 * j < n_kept) ? x : HFA_NEG_INF;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) mx = fmaxf(mx, xv[j]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)             // entries past the end are -inf: exp = +0, sum unchanged
+        sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(xv[j], mx)));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Persistent, TMA-fed variant of the kernel above -- the default whenever the logits rows of an
 // utterance are contiguous (unit column stride, which is what the [T, V+2] head-output views are).
@@ -381,21 +402,16 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
             const int part = lane & 3;
             float mx = HFA_NEG_INF, sum = 0.0f;
             if (n_kept <= 64) {                                              // CTA-uniform
-                // the lane's kept ids sit in registers (kreg, set up per utterance): one load per
-                // logit, reused by both passes; same order of operations as the loop below
-                float xv[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {       // unconditional load (kreg is 0 past the end) + select:
-                    const float x = hfa_to_float<TIn>(row[kreg[j]]);      // no divergent branches
-                    xv[j] = (part + 4 * j < n_kept) ? x : HFA_NEG_INF;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, xv[j]);
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-#pragma unroll
-                for (int j = 0; j < 16; ++j)         // entries past the end are -inf: exp = +0, sum unchanged
-                    sum = __fadd_rn(sum, hfa_exp_neg(__fsub_rn(xv[j], mx)));
+                // the lane's kept ids sit in registers (kreg, set up per utterance): one load per logit, reused
+                // by both passes; same order of operations as the loop below.  Only as many slots as the
+                // utterance has kept ids (4 lanes x NJ): slots past the end would add exp(-inf) = +0, the sums
+                // are bit-identical -- the kernel is issue-bound, a typical utterance keeps 40-50 ids.
+                const int nj = (n_kept + 3) >> 2;
+                if (nj <= 8) hfa_row_stats<8, TIn>(row, kreg, part, n_kept, mx, sum);
+                else if (nj <= 10) hfa_row_stats<10, TIn>(row, kreg, part, n_kept, mx, sum);
+                else if (nj <= 12) hfa_row_stats<12, TIn>(row, kreg, part, n_kept, mx, sum);
+                else if (nj <= 14) hfa_row_stats<14, TIn>(row, kreg, part, n_kept, mx, sum);
+                else hfa_row_stats<16, TIn>(row, kreg, part, n_kept, mx, sum);
             } else {
                 for (int k = part; k < n_kept; k += 4) mx = fmaxf(mx, hfa_to_float<TIn>(row[kept_sm[k]]));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
