@@ -335,6 +335,7 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
     int cur_u = -1;
     int S = 0, Sp = 4, T = 0, n_kept = 0;
     uint32_t goff[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int lpr = 32;
     int kreg[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) kreg[j] = 0;
@@ -373,9 +374,12 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
                 for (int w = 0; w < (tid >> 5); ++w) pos += __popc(mask_sm[w]);
                 kept_sm[pos] = tid;
             }
+            // lanes per stored row in the gather (D): a row of <= 32 / <= 64 columns (the compacted rows of big
+            // batches, short phoneme sequences) takes 8 / 16 lanes x float4, so a warp gathers 4 / 2 rows per pass
+            lpr = (Sp <= 32) ? 8 : (Sp <= 64) ? 16 : 32;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
-                const int s4 = min(lane * 4 + 128 * it, Sp - 4);
+                const int s4 = min((lane & (lpr - 1)) * 4 + 128 * it, Sp - 4);
                 const int4 id4 = *reinterpret_cast<const int4 *>(ids_sm + s4);
                 goff[it][0] = (uint32_t)id4.x; goff[it][1] = (uint32_t)id4.y;
                 goff[it][2] = (uint32_t)id4.z; goff[it][3] = (uint32_t)id4.w;
@@ -435,6 +439,28 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
                 const float x = (id < (uint32_t)V) ? hfa_to_float<TIn>(row[id]) : HFA_NEG_INF;
                 return __fsub_rn(__fsub_rn(x, st.x), st.y);
             };
+            if (lpr < 32) {                                                  // CTA-uniform: narrow rows
+                // lane -> (row r0 + lane / lpr, columns 4 (lane % lpr) ..): 4 or 2 rows per pass; same values, same
+                // order of operations per element as the one-row-per-pass loop below
+                const int sub = (lpr == 8) ? (lane >> 3) : (lane >> 4);
+                const int col = (lane & (lpr - 1)) * 4;
+                const int rpp = 32 / lpr;
+                const bool stc = col < Sp;
+                float *dst_n = ws.emis + m.emis_off + (int64_t)(t_base + RPW * warp) * Sp + col;
+#pragma unroll
+                for (int r0 = 0; r0 < RPW; r0 += 2) {
+                    if (r0 >= rows_here) break;                              // warp-uniform
+                    if (rpp == 4 && (r0 & 2)) continue;                      // uniform: 4 rows per pass -> r0 = 0, 4
+                    const int r = r0 + sub;
+                    const int rr = RPW * warp + r;
+                    const float2 st = stat_sm[rr];
+                    const TIn *row = xs + rr * row_st;
+                    float4 o;
+                    o.x = val(row, goff[0][0], st); o.y = val(row, goff[0][1], st);
+                    o.z = val(row, goff[0][2], st); o.w = val(row, goff[0][3], st);
+                    if (stc && r < rows_here) *reinterpret_cast<float4 *>(dst_n + r * dst_step) = o;
+                }
+            } else {
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 if (r >= rows_here) break;                                   // warp-uniform
@@ -450,6 +476,7 @@ hfa_emission_stream_kernel(HfaWs ws, int n_blocks, int V, int sp_cap, int stage_
                     o.z = val(row, goff[1][2], st); o.w = val(row, goff[1][3], st);
                     if (st1) *reinterpret_cast<float4 *>(dst + r * dst_step + 128) = o;
                 }
+            }
             }
             if (Sp > 256) {                                                  // long phoneme sequences
                 for (int r = 0; r < rows_here; ++r) {
