@@ -76,13 +76,22 @@ def workload_shapes(name: str, seed: int, corpus: int = 0):
     return T, S, V, desc
 
 
-def make_config(name, desc, T, S, world, extra=None):
-    """The `config` object -- the SAME keys in our arm and in the reference arm."""
+def make_config(name, desc, T, S, world, V):
+    """The `config` object -- IDENTICAL in our arm and in the reference arm (everything in it follows from the
+    workload alone; what only our arm knows -- collation, launch mode, chunking -- goes to `run_config`)."""
     from hubertfa_b200 import synth
+    frames = int(T.sum(dtype=np.int64))
     cfg = {"workload": f"{name}: {desc}", "utterances": int(len(T)), "cells": int((T.astype(np.int64) * S).sum()),
-           "frames": int(T.sum(dtype=np.int64)), "frame_seconds": synth.FRAME_SECONDS, "n_ranks": int(world)}
-    if extra:
-        cfg.update(extra)
+           "frames": frames, "frame_seconds": synth.FRAME_SECONDS, "n_ranks": int(world)}
+    in_mb = frames * (V + 2) * 4 / 1e6                       # f32 head output [sum T, V+2]
+    if name == "c5":
+        cfg["l2"] = ("GPU arm: inputs larger than L2 (%.1f GB of logits per rank and pass, 126 MB L2)"
+                     % (in_mb / 1e3 / max(int(world), 1)))
+    else:
+        n_sets = N_SETS if len(T) <= 512 else 2
+        cfg["l2"] = ("GPU arm: %d rotating input sets of %.1f MB of logits each, plus their workspaces -- consecutive "
+                     "steps touch different memory (inputs alone %.0f MB in rotation, 126 MB L2)"
+                     % (n_sets, in_mb, n_sets * in_mb))
     return cfg
 
 
@@ -196,7 +205,7 @@ def run_reference(args, rank, world):
     T, S, V, desc = workload_shapes(name, synth.SEED0, args.corpus)
     ids_list = (synth.make_ids_corpus(S, V, seed=synth.SEED0) if name == "c5"
                 else synth.make_ids_batch(T, S, V, seed=synth.SEED0))
-    cfg = make_config(name, desc, T, S, args.gpus)
+    cfg = make_config(name, desc, T, S, args.gpus, V)
     sample = "the full batch"
     if name == "c5":      # bounded sample of the corpus: its first 2048 utterances
         T, S, ids_list = corpus_sample(T, S, ids_list, 2048)
@@ -684,11 +693,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "audio_hours_per_s": m["frames"] * synth.FRAME_SECONDS / 3600 * args.steps / sec,
-            "config": make_config(wl, m["desc"], m["T"], m["S"], 1, {
+            "config": make_config(wl, m["desc"], m["T"], m["S"], 1, m["V"]),
+            "run_config": {
                 "collation": "batch packed longest utterance first",
                 "launch_mode": m["launch_mode"],
                 "l2": f"{m['n_sets']} rotating input+workspace sets of {m['bytes_per_set'] / 1e6:.0f} MB "
-                      "(consecutive steps touch different memory; total > 126 MB L2)"}),
+                      "(consecutive steps touch different memory)"},
             "clocks": m["clk"], "e2e": m["e2e"], "gpu_launches": int(m["launches"]),
             "roofline": roofline(m, wl), "verified": m["verified"],
         }
@@ -737,7 +747,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": c["ms"] / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "audio_hours_per_s": cp.frames * synth.FRAME_SECONDS / 3600 * args.steps / sec,
-            "config": make_config("c5", c["desc"], c["T"], c["S"], world, {
+            "config": make_config("c5", c["desc"], c["T"], c["S"], world, c["V"]),
+            "run_config": {
                 "sharding": "shard_by_cost (LPT over T*S) -> chunks of <= %d cells -> hfa_align_batch per chunk on two "
                             "alternating streams -> D2H into a shared pinned host segment -> barrier: rank 0 holds "
                             "all results; no collective on the data path" % CORPUS_CHUNK_CELLS,
@@ -745,7 +756,7 @@ def main():
                 "cells_per_rank": [cp.cells_of_rank(r) for r in range(world)],
                 "logits": "the whole corpus generated on every GPU from one seeded device generator; a rank reads only "
                           "its own utterances (inputs larger than L2: %.1f GB per rank)"
-                          % (cp.frames * (c["V"] + 2) * 4 / world / 1e9)}),
+                          % (cp.frames * (c["V"] + 2) * 4 / world / 1e9)},
             "clocks": c["clk"], "e2e": c["e2e"], "gpu_launches": int(c["launches"]),
             "all_status_ok": c["ok"], "verified": c["verified"], "cpu_baseline": None,
         }

@@ -9,6 +9,6 @@ for f in ["c5_${N}gpu","ref_${N}gpu"]:
     try:
         d=json.loads([l for l in open(f"gpurun_out/bench_{f}.json").read().strip().splitlines() if l.startswith("{")][-1])
         print(f, json.dumps({k:d[k] for k in d if k not in ("config",)}, indent=0)[:3000])
-        print(d["config"].get("chunks_per_rank"), d["config"].get("cells_per_rank"))
+        print(d["run_config"].get("chunks_per_rank"), d["run_config"].get("cells_per_rank"))
     except Exception as e: print(f, "ERR", e)
 PY

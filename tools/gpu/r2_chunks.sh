@@ -6,7 +6,7 @@ for cc in 150000000 100000000 75000000 50000000 37500000; do
 import json
 try:
     d=json.loads(open("gpurun_out/chunks_${cc}_$ns.json").read().strip().splitlines()[-1])
-    print("chunk $cc streams $ns: ms %.4f value %.4g chunks %s launches %d" % (d["ms_per_step"], d["value"], d["config"]["chunks_per_rank"], d["gpu_launches"]))
+    print("chunk $cc streams $ns: ms %.4f value %.4g chunks %s launches %d" % (d["ms_per_step"], d["value"], d["run_config"]["chunks_per_rank"], d["gpu_launches"]))
 except Exception as e: print("chunk $cc streams $ns ERR", e)
 PY
  done

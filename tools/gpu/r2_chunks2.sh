@@ -5,7 +5,7 @@ run() { # corpus cc ns
 import json
 try:
     d=json.loads(open("gpurun_out/chunks2.json").read().strip().splitlines()[-1])
-    print("corpus $1 chunk $2 streams $3: ms %.4f value %.4g chunks %s" % (d["ms_per_step"], d["value"], d["config"]["chunks_per_rank"]))
+    print("corpus $1 chunk $2 streams $3: ms %.4f value %.4g chunks %s" % (d["ms_per_step"], d["value"], d["run_config"]["chunks_per_rank"]))
 except Exception as e: print("corpus $1 chunk $2 streams $3 ERR", e, open("gpurun_out/chunks2.err").read()[-300:])
 PY
 }

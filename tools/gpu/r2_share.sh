@@ -10,6 +10,6 @@ import json,glob
 for f in sorted(glob.glob("gpurun_out/r2s/s_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f.split("/")[-1], "ms %.3f"%d["ms_per_step"], "value %.4g"%d["value"], d["config"]["chunks_per_rank"])
+        print(f.split("/")[-1], "ms %.3f"%d["ms_per_step"], "value %.4g"%d["value"], d["run_config"]["chunks_per_rank"])
     except Exception as e: print(f, "ERR", e)
 PY
